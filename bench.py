@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py — E_loc state·term couplings/sec on B200 (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload n2_1e6|h2o_1e5|li2o_1e5|synthetic]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's CPU path (oracle/_ref Cython kernels) on the host cores
+
+A "step" = one pass of the hot path over one batch: (all-gather of the (key, psi) shards when N > 1) ->
+amplitude-lookup build -> fused E_loc kernel -> E_loc statistics (-> all-reduce of 5 fp64 scalars when N > 1).
+`value`  : couplings/s (M·K per step, summed over ranks) with the inputs already resident in HBM, CUDA-event timed.
+`e2e`    : the same metric through the host-buffer entry (pinned host states + psi in, E_loc out), copies inside the timed region.
+Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+METRIC = "eloc_state_term_couplings_per_sec"
+UNIT = "couplings/s"
+
+
+# ----------------------------------------------------------------------------------------- workloads
+def load_table(mol):
+    d = np.load(os.path.join(GOLDEN, "tables", f"{mol}.npz"))
+    N, na, nb = (int(x) for x in d["meta"])
+    return d["xy"], d["yz"], d["coeff"], N, na, nb
+
+
+def psi_for(n, seed):
+    rng = np.random.default_rng(seed)
+    return (rng.normal(size=n) + 1j * rng.normal(size=n)).astype(np.complex64)
+
+
+def sector_states(N, na, nb, m, seed):
+    rng = np.random.default_rng(seed)
+    ev, od = np.arange(0, N, 2), np.arange(1, N, 2)
+    a = np.zeros(2 * m, np.int64)
+    for arr, k in ((ev, na), (od, nb)):
+        picks = np.argsort(rng.random((2 * m, len(arr))), axis=1)[:, :k]
+        a |= (1 << arr[picks]).sum(axis=1)
+    a = np.unique(a)
+    return rng.permutation(a)[:m].astype(np.uint64)
+
+
+def synthetic_table(N, K, seed=0):
+    """Random Pauli sum of SURVEY.md §8d config 5: 2-/4-qubit flip masks shared by ~6 terms each (+ a diagonal group),
+    YZ masks = JW-like contiguous run XOR a random weight-N/4 mask, normal fp64 coefficients."""
+    rng = np.random.default_rng(seed)
+    W = 1 if N <= 63 else 2
+    G = max(2, K // 6)
+    flips = [0]
+    for _ in range(G - 1):
+        qs = rng.choice(N, 2 if rng.random() < 0.3 else 4, replace=False)
+        flips.append(sum(1 << int(q) for q in qs))
+    xy, yz = [], []
+    for k in range(K):
+        f = flips[k % G]
+        lo, hi = sorted(int(q) for q in rng.choice(N, 2, replace=False))
+        run = ((1 << hi) - 1) ^ ((1 << lo) - 1)
+        rnd = int.from_bytes(np.packbits(rng.random(8 * ((N + 7) // 8)) < 0.25).tobytes(), "little") & ((1 << N) - 1)
+        xy.append(f)
+        yz.append((run ^ rnd) & ~f)
+    m64 = (1 << 64) - 1
+    to_words = lambda vals: np.array([[(v >> (64 * w)) & m64 for w in range(W)] for v in vals], dtype=np.uint64)  # noqa: E731
+    return to_words(xy), to_words(yz), rng.normal(size=K)
+
+
+def make_workload(name, rank, m_override=None, synth=None):
+    """-> dict(table args, states uint64 [M], psi complex64 [M], description).  Seeded; rank r draws seed r."""
+    if name == "n2_1e6":
+        xy, yz, c, N, _, _ = load_table("N2")
+        M = m_override or 1_000_000
+        st = np.random.default_rng(rank).choice(2 ** N, M, replace=False).astype(np.uint64)
+        desc = f"N2 STO-3G (20 qubits, K=2239, Kxy=378), M={M} distinct keys of the unrestricted 2^20 space per GPU (seed=rank), sector filter off, psi complex64 (SURVEY.md §8d config 3)"
+        return dict(xy=xy, yz=yz, c=c, N=N, na=None, nb=None, states=st, psi=psi_for(M, rank), desc=desc, mol="N2")
+    if name == "h2o_1e5":
+        xy, yz, c, N, _, _ = load_table("H2O")
+        M = m_override or 100_000
+        st = np.random.default_rng(rank).integers(0, 2 ** N, M).astype(np.uint64)
+        desc = f"H2O STO-3G (14 qubits, K=1390), M={M} rows drawn with replacement from 2^14 (1e5 unique 14-qubit states do not exist), table = distinct keys (SURVEY.md §8d config 2)"
+        return dict(xy=xy, yz=yz, c=c, N=N, na=None, nb=None, states=st, psi=psi_for(M, rank), desc=desc, mol="H2O", dedup_table=True)
+    if name == "li2o_1e5":
+        xy, yz, c, N, na, nb = load_table("Li2O")
+        M = m_override or 100_000
+        st = sector_states(N, na, nb, M, rank)
+        desc = f"Li2O STO-3G (30 qubits, K=20558, Kxy=3810), M={M} distinct (7,7)-sector states per GPU, sector filter on (SURVEY.md §8d config 4 batch)"
+        return dict(xy=xy, yz=yz, c=c, N=N, na=na, nb=nb, states=st, psi=psi_for(M, rank), desc=desc, mol="Li2O")
+    if name == "synthetic":
+        N, K, M = synth
+        xy, yz, c = synthetic_table(N, K)
+        rng = np.random.default_rng(rank)
+        W = 1 if N <= 63 else 2
+        st = np.zeros((M, W), np.uint64)
+        bits = np.argsort(rng.random((M, N)), axis=1)[:, : N // 2]
+        for w in range(W):
+            sel = (bits >= 64 * w) & (bits < 64 * (w + 1))
+            st[:, w] = np.where(sel, np.uint64(1) << np.where(sel, bits - 64 * w, 0).astype(np.uint64), np.uint64(0)).sum(axis=1, dtype=np.uint64)
+        st = np.unique(st, axis=0)
+        st = st[rng.permutation(len(st))]
+        desc = f"synthetic Pauli sum: N={N} qubits, K={K} terms (Kxy~K/6), M={len(st)} random weight-N/2 keys per GPU (SURVEY.md §8d config 5)"
+        return dict(xy=xy, yz=yz, c=c, N=N, na=None, nb=None, states=st, psi=psi_for(len(st), rank), desc=desc, mol="synthetic")
+    raise SystemExit(f"unknown workload {name}")
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock + throttle reasons of one GPU (NVML) while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        self.index, self.period, self.samples, self.reasons = index, period, [], set()
+        self._stop = threading.Event()
+        self._t = None
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(statistics.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def pipe_peaks():
+    """Integer / fp64 pipe ceilings measured with bench_tools/pipe_peaks.cu on this pool's B200 (profiles/)."""
+    for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True) if os.path.isdir(os.path.join(ROOT, "profiles")) else []:
+        if name.startswith("pipe_peaks") and name.endswith(".json"):
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return json.load(f), name
+    return None, None
+
+
+# ----------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's own CPU implementation of the path (compiled Cython kernels from oracle/_ref + the numpy/scipy
+    orchestration of hamiltonian.py:272-370 restated in oracle/ref_path.py), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import ref_path
+    wl = make_workload(args.workload, 0, m_override=args.ref_sample)
+    M, K = len(wl["states"]), len(wl["c"])
+    path = ref_path.ReferencePath(wl["xy"], wl["yz"], wl["c"], wl["N"], wl["na"], wl["nb"])
+    st = wl["states"].astype(np.int64)
+    times = []
+    for i in range(args.warmup + args.steps):
+        path.reset()  # cold H cache: first-seen states, the steady state for large molecules
+        t0 = time.perf_counter()
+        path.local_energy(st, wl["psi"])
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = M * K * len(times) / total
+    cores = os.cpu_count()
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "sample": f"{M} of the workload's states per step, cold H cache each step"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                             "sample": f"{M} states x K={K} per step; reference Cython kernels (oracle/_ref) + numpy/scipy orchestration, OMP threads={cores}"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def cpu_baseline_sample(wl, sample, reps=2):
+    from oracle import ref_path
+    M = min(sample, len(wl["states"]))
+    path = ref_path.ReferencePath(wl["xy"], wl["yz"], wl["c"], wl["N"], wl["na"], wl["nb"])
+    st, psi = wl["states"][:M].astype(np.int64).reshape(-1), wl["psi"][:M]
+    best = None
+    for _ in range(reps):
+        path.reset()
+        t0 = time.perf_counter()
+        path.local_energy(st, psi)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    K = len(wl["c"])
+    return {"value": M * K / best, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+            "sample": f"first {M} states of the workload, K={K}, cold H cache, best of {reps}: {best:.2f} s "
+                      f"(reference Cython kernels from oracle/_ref + numpy/scipy orchestration of hamiltonian.py:272-370)"}
+
+
+# ----------------------------------------------------------------------------------------- B200 arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="n2_1e6")
+    ap.add_argument("--states", type=int, default=None, help="override M (states per GPU)")
+    ap.add_argument("--synthetic", type=int, nargs=3, default=[64, 10000, 100000], metavar=("N", "K", "M"))
+    ap.add_argument("--cpu-sample", type=int, default=100_000, help="states of the bounded cpu_baseline sample (0 = skip)")
+    ap.add_argument("--ref-sample", type=int, default=50_000, help="states per step of --impl reference")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import naqs_b200
+    from naqs_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch N>1 with torch.distributed.run (one process per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = make_workload(args.workload, rank, m_override=args.states, synth=tuple(args.synthetic))
+    table = naqs_b200.DeviceTermTable(wl["xy"], wl["yz"], wl["c"], wl["N"], wl["na"], wl["nb"], device=dev)
+    M, K, W = len(wl["states"]), table.K, table.words
+    h_states = torch.from_numpy(np.ascontiguousarray(wl["states"]).reshape(M, W).view(np.int64)).pin_memory()
+    h_psi = torch.from_numpy(wl["psi"]).pin_memory()
+    d_states, d_psi = h_states.to(dev), h_psi.to(dev)
+    d_eloc = torch.empty((M, 2), dtype=torch.float64, device=dev)
+    h_eloc = torch.empty((M, 2), dtype=torch.float64).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    if world > 1:
+        g_states = torch.empty((world * M, W), dtype=torch.int64, device=dev)
+        g_psi = torch.empty(world * M, dtype=torch.complex64, device=dev)
+    dedup = wl.get("dedup_table", False)
+    if dedup:  # H2O "with replacement" workload: the lookup table is the distinct keys (fixed across steps)
+        uk, first = np.unique(wl["states"], return_index=True)
+        t_keys = torch.from_numpy(uk.view(np.int64)).to(dev).reshape(-1, 1)
+        t_psi = d_psi[torch.from_numpy(first).to(dev)]
+
+    def step(states, psi, out):
+        """One pass of the hot path with device-resident inputs; returns the 5 statistics sums (device)."""
+        if world > 1:
+            dist.all_gather_into_tensor(g_states, states)
+            dist.all_gather_into_tensor(g_psi, psi)
+            table.build_lookup(g_states, g_psi)
+        elif dedup:
+            table.build_lookup(t_keys, t_psi)
+        else:
+            table.build_lookup(states, psi)
+        ev_k0.record()
+        table.local_energy(states, psi, out=out, rebuild_lookup=False)
+        ev_k1.record()
+        s5 = table.stats(out)
+        if world > 1:
+            dist.all_reduce(s5)
+        return s5
+
+    ev_k0, ev_k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----------------------------------------------------------------
+    for _ in range(args.warmup):
+        flush.fill_(1)
+        step(d_states, d_psi, d_eloc)
+    barrier()
+    step_ms, kern_ms = [], []
+    launches0 = naqs_b200.launch_count()
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        for _ in range(args.steps):
+            flush.fill_(1)  # L2 flush between timed iterations (untimed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            s5 = step(d_states, d_psi, d_eloc)
+            e1.record()
+            e1.synchronize()
+            step_ms.append(e0.elapsed_time(e1))
+            kern_ms.append(ev_k0.elapsed_time(ev_k1))
+        barrier()
+    launches = naqs_b200.launch_count() - launches0
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = world * M * K * args.steps / (total_ms * 1e-3)
+    stats = s5.cpu().numpy()
+
+    # ---- end to end through the host-buffer public API -----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            if world == 1 and not dedup:
+                return table.local_energy_host(h_states.numpy().view(np.uint64), h_psi.numpy())
+            ds, dp = h_states.to(dev, non_blocking=True), h_psi.to(dev, non_blocking=True)
+            step(ds, dp, d_eloc)
+            h_eloc.copy_(d_eloc, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return h_eloc
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(5, min(args.steps, 50))
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * M * K * n_e2e / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(M * (8 * W + 8)),
+               "d2h_bytes_per_step": int(M * 16), "steps": n_e2e,
+               "api": "DeviceTermTable.local_energy_host -> naqs_eloc_host (host numpy in, complex128 E_loc out)" if world == 1 and not dedup
+                      else "pinned H2D + step + pinned D2H of E_loc"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline + cpu baseline (rank 0) -------------------------------------------------------
+    peaks, peak_src = measured_peaks()
+    k_ms = float(np.mean(kern_ms))
+    T = (world * M) if not dedup else int(t_keys.shape[0])
+    algo_bytes = M * (8 * W + 8 + 16) + K * (16 * W + 8) + min(T, 2 ** wl["N"]) * 16  # states+psi in, E_loc out, Pauli table, lookup entries touched
+    achieved_gbs = algo_bytes / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"],
+                "traffic": None, "peak_source": peak_src, "kernel": "eloc_direct_kernel", "kernel_ms": k_ms,
+                "note": "HBM is not the binding resource (0.03 B/coupling, SURVEY.md §8d); see roofline_pipe"}
+    pp, pp_name = pipe_peaks()
+    kernel_rate = M * K / (k_ms * 1e-3)
+    roofline_pipe = {"kernel_couplings_per_s": kernel_rate, "peak": None, "frac": None}
+    if pp:
+        roofline_pipe = {"bound": "popc+issue (direct formulation: AND, POPC, SHL, XOR, DADD per coupling)",
+                         "kernel_couplings_per_s": kernel_rate, "peak": pp.get("direct_couplings_per_s"), "unit": UNIT,
+                         "frac": kernel_rate / pp["direct_couplings_per_s"] if pp.get("direct_couplings_per_s") else None,
+                         "popc_ops_per_s": pp.get("popc_ops_per_s"), "dadd_ops_per_s": pp.get("dadd_ops_per_s"), "peak_source": f"profiles/{pp_name}"}
+    cpu = None
+    if world == 1 and args.cpu_sample > 0:
+        try:
+            cpu = cpu_baseline_sample(wl, args.cpu_sample)
+        except Exception as e:  # noqa: BLE001
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": wl["desc"], "states_per_gpu": M, "terms": K, "lookup_keys": T,
+                       "parallelism": f"states sharded x{world}, Pauli table replicated" + (", NCCL all-gather of (key, psi) + all-reduce of 5 fp64 sums" if world > 1 else ""),
+                       "l2": "256 MB device memset between timed steps (L2 flush, untimed)", "timing": "CUDA events per step on the launching stream, max over ranks"},
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_pipe": roofline_pipe,
+            "cpu_baseline": cpu,
+            "check": {"mean_eloc_re": float(stats[1] / stats[0]), "n": int(stats[4])}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,162 @@
+/* naqs_eloc.h — C ABI of the B200-native NAQS local-energy (E_loc) hot path.
+ *
+ * Drop-in boundary for the three compiled extension modules the reference imports by name
+ * (src_cpp/setup.py:36-38: src.utils.hamiltonian_math / sparse_math / hilbert_math) and for the
+ * numpy/scipy orchestration around them (src/optimizer/hamiltonian.py:272-370,
+ * src/optimizer/energy.py:219-263).  All paths below are relative to the reference root.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / numpy / C++ types.  Every entry returns an int status
+ *     (NAQS_OK = 0); naqs_last_error() gives the message of the calling thread's last failure.
+ *     The Python shims map NAQS_ERR_DTYPE -> TypeError (hamiltonian_math.pyx:484) and the other
+ *     codes -> RuntimeError / ValueError.
+ *   - `d_` pointers are device memory of the table's device; `h_` pointers are host memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are asynchronous
+ *     and stream-ordered unless stated otherwise; the caller owns every buffer it passes, the
+ *     library owns only the table handle and its internal workspace.
+ *   - a state / mask key is `words` consecutive uint64 (word 0 = qubits 0..63); bit q set <=> qubit q
+ *     occupied (src/utils/hilbert.py:425,576-577).  words = 1 for n_qubits <= 63, 2 for <= 127.
+ *   - complex numbers are interleaved (re, im) doubles (numpy complex128 / torch [...,2] float64).
+ *   - there is NO CPU fallback anywhere in this library: without a CUDA device every compute entry
+ *     fails with NAQS_ERR_CUDA.
+ */
+#ifndef NAQS_ELOC_H
+#define NAQS_ELOC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NAQS_ABI_VERSION 1
+
+enum {
+    NAQS_OK = 0,
+    NAQS_ERR_ARG = 1,    /* bad argument (null pointer, size, unsupported width)            */
+    NAQS_ERR_DTYPE = 2,  /* unsupported element type (-> TypeError in the Python shims)     */
+    NAQS_ERR_CUDA = 3,   /* CUDA runtime / launch failure, or no device                    */
+    NAQS_ERR_ALLOC = 4,  /* out of memory (host or device)                                 */
+    NAQS_ERR_STATE = 5   /* call order violated (e.g. E_loc before a lookup table was set) */
+};
+
+/* psi element types of naqs_lookup_build / naqs_eloc */
+enum { NAQS_C128 = 0, NAQS_C64 = 1 };
+
+/* lookup-table organisations (naqs_lookup_build `kind`; NAQS_LOOKUP_AUTO picks by n_qubits) */
+enum { NAQS_LOOKUP_AUTO = 0, NAQS_LOOKUP_DENSE = 1, NAQS_LOOKUP_HASH = 2 };
+
+typedef struct naqs_table naqs_table_t; /* opaque, device resident */
+
+const char* naqs_last_error(void);
+int naqs_abi_version(void);
+/* number of CUDA devices visible (0 without a driver); never fails */
+int naqs_device_count(void);
+/* kernels launched by this library in the calling process since load (bench.py's gpu_launches) */
+int64_t naqs_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Term table  — replaces _PauliHamiltonianDynamic.__init__ / __calc_coupling_info's outputs
+ * (src/optimizer/hamiltonian.py:241-252, 373-430): xy[k], yz[k], coeff[k] in REFERENCE TERM ORDER.
+ * The table groups terms by XY mask (np.unique order, hamiltonian.py:248) keeping ascending k
+ * inside a group, so that every H_ij is accumulated in exactly the order of
+ * src_cpp/hamiltonian_math.pyx:31-34.
+ * n_alpha / n_beta < 0  => no sector filter (the _HilbertFull case, src/utils/hilbert.py:377-378);
+ * otherwise coupled states must carry n_alpha bits on even and n_beta bits on odd qubits
+ * (src/utils/hilbert.py:446-449; filter of hamiltonian.py:321-328).
+ * Host pointers; synchronous. */
+int naqs_table_create(naqs_table_t** out, const uint64_t* h_xy, const uint64_t* h_yz, const double* h_coeff,
+                      int64_t n_terms, int words, int n_qubits, int n_alpha, int n_beta, int device);
+int naqs_table_destroy(naqs_table_t* t);
+/* info[0..7] = K, Kxy (unique XY masks), Kyz (unique YZ masks), words, n_qubits, n_alpha, n_beta, device */
+int naqs_table_info(const naqs_table_t* t, int64_t* info8);
+
+/* ------------------------------------------------------------------------------------------
+ * Amplitude lookup table — replaces the "is s' among the sampled states, and what is psi(s')" step
+ * that the reference performs with scipy fancy indexing H[idx[:,None], idx]
+ * (src/optimizer/hamiltonian.py:93-111 get_H; or the merge-join of src_cpp/sparse_math.pyx:316-342).
+ * Builds, on `stream`, an internal device structure from T (key, psi) pairs.  Duplicate keys are
+ * summed, as scipy's repeated column would be.  The table stays valid until the next build. */
+int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi, int psi_dtype,
+                      int64_t n_keys, int kind, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused local energy — replaces OptimizerBase.calculate_local_energy's body
+ * (src/optimizer/energy.py:245-248): update_H + get_H + sparse_dense_mv + "/ psi" + conj.
+ *   E_loc[m] = conj( sum_{u} H[s_m, s_m^u] * psi_table(s_m^u) / psi[m] ),
+ *   H[s, s^u] = sum_{k: xy_k = u} coeff_k * (-1)^popcount(s & yz_k)        (k ascending)
+ * over the unique XY masks u whose coupled state passes the sector filter and whose H is not
+ * exactly 0.0 (hamiltonian.py:328,363); coupled states absent from the lookup table contribute 0
+ * (energy.py:247, set_unsampled_states_to_zero=True).  complex128 arithmetic
+ * (src_cpp/sparse_math.pyx:33-37).  d_eloc: M interleaved complex128.
+ * Requires a prior naqs_lookup_build on the same table. */
+int naqs_eloc(naqs_table_t* t, const uint64_t* d_states, const void* d_psi, int psi_dtype, int64_t n_states,
+              double* d_eloc, void* stream);
+
+/* Same through HOST buffers (what a caller holding numpy arrays uses; bench.py's e2e leg): uploads
+ * states + psi, builds the lookup table from the same (states, psi) batch, runs naqs_eloc and
+ * downloads E_loc.  Synchronous.  h_table_keys may be NULL (=> the batch is its own table, the
+ * reference's only mode) or T separate (key, psi) pairs. */
+int naqs_eloc_host(naqs_table_t* t, const uint64_t* h_states, const void* h_psi, int psi_dtype, int64_t n_states,
+                   const uint64_t* h_table_keys, const void* h_table_psi, int64_t n_table,
+                   double* h_eloc);
+
+/* ------------------------------------------------------------------------------------------
+ * Stored Hamiltonian rows (CSR / coupled-set mode) — replaces update_H's row construction
+ * (src/optimizer/hamiltonian.py:301-363) and get_coupled_state_idxs (:122-132).
+ * Two passes: count -> (caller or naqs_exclusive_scan) -> fill.  A stored entry is a coupled state
+ * that passes the sector filter with H != 0.0.  Columns of a row come in ascending unique-XY order.
+ * d_col_ridx (optional, may be NULL) receives the restricted index of each column
+ * (src/utils/hilbert.py:607-640 full2restricted_idx; = low key word without a sector). */
+int naqs_rows_count(naqs_table_t* t, const uint64_t* d_states, int64_t n_states, int64_t* d_counts, void* stream);
+int naqs_exclusive_scan(naqs_table_t* t, const int64_t* d_counts, int64_t n, int64_t* d_indptr /* n+1 */, void* stream);
+int naqs_rows_fill(naqs_table_t* t, const uint64_t* d_states, int64_t n_states, const int64_t* d_indptr,
+                   uint64_t* d_col_keys, int64_t* d_col_ridx, double* d_vals, void* stream);
+/* dense H_ij[M*Kxy] exactly as get_Hij_cy returns it (src_cpp/hamiltonian_math.pyx:200-288),
+ * i.e. before the sector mask and without dropping zeros */
+int naqs_hij_dense(naqs_table_t* t, const uint64_t* d_states, int64_t n_states, double* d_hij, void* stream);
+/* sorted unique union of keys (np.unique of hamiltonian.py:131): LSD radix sort + adjacent-unique.
+ * d_out holds up to n keys; *h_n_unique is written after an internal stream sync. */
+int naqs_unique_keys(naqs_table_t* t, const uint64_t* d_keys, int64_t n, uint64_t* d_out, int64_t* h_n_unique, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Level-0 shims: function-for-function twins of the Cython entry points, on device buffers. */
+/* popcount_parity (src_cpp/hamiltonian_math.pyx:455-484): out[i] = 1 - 2*(popcount(in[i]) & 1);
+ * itemsize in {1,2,4,8} (signed or unsigned: the bit pattern decides), else NAQS_ERR_DTYPE. */
+int naqs_popcount_parity(const void* d_in, int itemsize, int64_t n, int8_t* d_out, void* stream);
+/* get_Hij_cy (src_cpp/hamiltonian_math.pyx:200-288): H_ij[m*Kxy + u2a_xy[k]] += P[m, u2a_yz[k]] * c[k],
+ * k ascending.  coeff_itemsize 8 (float64) or 4 (float32), output of the same type, else NAQS_ERR_DTYPE. */
+int naqs_get_hij(int64_t n_states, int64_t n_xy, int64_t n_yz, int64_t n_terms, const int64_t* d_u2a_xy,
+                 const int8_t* d_parity, const int64_t* d_u2a_yz, const void* d_coeff, int coeff_itemsize,
+                 void* d_hij, void* stream);
+/* sparse_dense_mv (src_cpp/sparse_math.pyx:49-243): out[r] = sum_e data[e] * v[indices[e]] over CSR row r,
+ * accumulated in storage order.  data float64/float32 (data_itemsize 8/4), v and out complex of twice that
+ * width, indices/indptr int32 or int64 (idx_itemsize 4/8). */
+int naqs_sparse_dense_mv(const void* d_data, int data_itemsize, const void* d_indices, const void* d_indptr,
+                         int idx_itemsize, int64_t n_rows, const void* d_v, void* d_out, void* stream);
+/* sparse_sparse_mv (src_cpp/sparse_math.pyx:251-402): out[k] = sum over row v_idxs[k] of data * v[pos(col)]
+ * for the columns present in the SORTED v_idxs list (binary search replaces the merge-join). */
+int naqs_sparse_sparse_mv(const void* d_data, int data_itemsize, const void* d_indices, const void* d_indptr,
+                          int idx_itemsize, const void* d_v, const void* d_v_idxs_sorted, int64_t n_v,
+                          void* d_out, void* stream);
+/* make_basis_idxs_cy (src_cpp/hilbert_math.pyx:12-44): out[i*N + j] = i & (1 << j), int32 [2^N, N] */
+int naqs_make_basis_idxs(int n_qubits, int32_t* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Hilbert-space encodings (src/utils/hilbert.py) */
+/* state2idx (hilbert.py:573-581): int8 rows [M, N] (occupied = value > 0) -> keys [M, words] */
+int naqs_state2idx(const int8_t* d_states, int64_t n_states, int n_qubits, int words, uint64_t* d_keys, void* stream);
+/* full2restricted_idx (hilbert.py:607-640) without the 2^N LUT: combinatorial rank in the
+ * reference's sector order (hilbert.py:446-469), -1 outside the sector */
+int naqs_restricted_index(naqs_table_t* t, const uint64_t* d_keys, int64_t n, int64_t* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * E_loc statistics (src/optimizer/energy.py:328,372-375), fp64:
+ * out5 = [sum w, sum w*Re E, sum w*Im E, sum w*(Re E)^2, n].  d_w may be NULL (w = 1).
+ * These five numbers are what the multi-GPU path all-reduces. */
+int naqs_eloc_stats(naqs_table_t* t, const double* d_eloc, const double* d_w, int64_t n, double* d_out5, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAQS_ELOC_H */

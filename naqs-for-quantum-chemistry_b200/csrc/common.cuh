@@ -1,0 +1,144 @@
+// common.cuh — shared declarations of libnaqs_eloc (sm_100a only).
+//
+// Internal layout of the device-resident Pauli table:
+//   terms are stored GROUP-MAJOR: groups = unique XY masks in ascending order (np.unique order of
+//   the reference, src/optimizer/hamiltonian.py:248), terms of a group in ascending reference index k,
+//   so a serial walk over a group reproduces the summation order of
+//   src_cpp/hamiltonian_math.pyx:31-34 bit for bit.
+//   Masks are held as NW32 32-bit words (NW32 = 1 for N<=32, 2 for N<=64, 4 for N<=128) in
+//   struct-of-arrays form so that a warp reads one word per term with a single broadcast LDS.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/naqs_eloc.h"
+
+namespace naqs {
+
+void set_error(const std::string& msg);
+extern std::atomic<int64_t> g_launches;
+
+#define NAQS_CUDA(call)                                                                         \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            naqs::set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                \
+            return e_ == cudaErrorMemoryAllocation ? NAQS_ERR_ALLOC : NAQS_ERR_CUDA;            \
+        }                                                                                       \
+    } while (0)
+
+#define NAQS_REQUIRE(cond, code, msg)                                                           \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            naqs::set_error(msg);                                                               \
+            return code;                                                                        \
+        }                                                                                       \
+    } while (0)
+
+// count + check a kernel launch
+#define NAQS_LAUNCHED()                                                                         \
+    do {                                                                                        \
+        naqs::g_launches.fetch_add(1, std::memory_order_relaxed);                               \
+        NAQS_CUDA(cudaGetLastError());                                                          \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// Sector description passed by value to kernels.  enabled == 0 => every key is "in sector".
+struct Sector {
+    uint32_t even[4];
+    uint32_t odd[4];
+    int n_alpha, n_beta, enabled, n_qubits;
+};
+
+// Group-major term table view (device pointers).
+struct TableView {
+    const uint32_t* yz;      // [NW32][K]   SoA: word w of term i at yz[w*K + i]
+    const double* coeff;     // [K]
+    const uint32_t* gxy;     // [NW32][G]
+    const uint32_t* gstart;  // [G+1]       term offsets of each group
+    int K, G;
+};
+
+// A shared-memory tile of the term table: terms [t0, t1) and the groups touching them [g0, g1).
+// A group may straddle two tiles; its partial sum is carried in registers.
+struct Tile {
+    uint32_t t0, t1;
+    uint32_t g0, g1;
+};
+
+// Hash slot: one 32-byte sector per probe.
+struct alignas(32) HashSlot {
+    unsigned long long key[2];
+    double re, im;
+};
+static_assert(sizeof(HashSlot) == 32, "HashSlot must be one 32 B sector");
+constexpr unsigned long long kEmptyKey = ~0ull;
+
+struct LookupView {
+    const double2* dense;    // [2^N] (kind DENSE)
+    const HashSlot* slots;   // [cap]  (kind HASH)
+    unsigned long long mask; // cap - 1
+    int kind;
+};
+
+__host__ __device__ inline unsigned long long mix64(unsigned long long x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+__host__ __device__ inline unsigned long long hash_key(unsigned long long k0, unsigned long long k1) {
+    return mix64(k0 ^ (k1 * 0x9E3779B97F4A7C15ULL));
+}
+
+}  // namespace naqs
+
+struct naqs_table {
+    int device = 0, words = 1, nw32 = 1, n_qubits = 0, n_alpha = -1, n_beta = -1;
+    int64_t K = 0, G = 0, Kyz = 0;
+    naqs::Sector sector{};
+    // device arrays
+    uint32_t* d_yz = nullptr;
+    double* d_coeff = nullptr;
+    uint32_t* d_gxy = nullptr;
+    uint32_t* d_gstart = nullptr;
+    naqs::Tile* d_tiles = nullptr;
+    int n_tiles = 0, tile_cap = 0;
+    long long* d_binom = nullptr;  // C(n, k) table for the restricted-index ranker (lazy)
+    // lookup
+    int lookup_kind = 0;  // 0 = none
+    int64_t lookup_n = 0;
+    double2* d_dense = nullptr;
+    int64_t dense_entries = 0;
+    naqs::HashSlot* d_slots = nullptr;
+    int64_t hash_cap = 0, hash_alloc = 0;
+    // generic workspace (scan / sort temporaries, host-path staging)
+    void* d_ws = nullptr;
+    size_t ws_bytes = 0;
+    void* d_stage = nullptr;  // device staging for naqs_eloc_host
+    size_t stage_bytes = 0;
+    void* h_pinned = nullptr;
+    size_t pinned_bytes = 0;
+    cudaStream_t own_stream = nullptr;
+
+    naqs::TableView view() const { return naqs::TableView{d_yz, d_coeff, d_gxy, d_gstart, (int)K, (int)G}; }
+    naqs::LookupView lookup() const {
+        return naqs::LookupView{d_dense, d_slots, (unsigned long long)(hash_cap - 1), lookup_kind};
+    }
+};
+
+namespace naqs {
+int ensure_ws(naqs_table* t, size_t bytes);
+}

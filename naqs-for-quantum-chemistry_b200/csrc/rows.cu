@@ -1,0 +1,132 @@
+// rows.cu — stored Hamiltonian rows (CSR / coupled-set mode), dense H_ij, restricted-index ranker,
+// exclusive scan and sorted-unique of keys.  C ABI documented in include/naqs_eloc.h.
+#include <vector>
+
+#include "common.cuh"
+#include "eloc_kernels.cuh"
+#include "sort_scan.cuh"
+
+using namespace naqs;
+
+namespace {
+
+constexpr int kRowThreads = 128;
+
+int ensure_binom(naqs_table* t) {
+    if (t->d_binom) return NAQS_OK;
+    std::vector<long long> b(65 * 66, 0);
+    for (int n = 0; n <= 64; ++n)
+        for (int k = 0; k < 66; ++k) {
+            long long v;
+            if (k == 0) v = 1;
+            else if (n == 0) v = 0;
+            else {
+                const long long a = b[(n - 1) * 66 + k - 1], c = b[(n - 1) * 66 + k];
+                v = (a > (1ll << 62) || c > (1ll << 62)) ? (1ll << 62) : a + c;  // saturate (unreachable for int64 sectors)
+            }
+            b[n * 66 + k] = v;
+        }
+    NAQS_CUDA(cudaMalloc((void**)&t->d_binom, b.size() * sizeof(long long)));
+    NAQS_CUDA(cudaMemcpy(t->d_binom, b.data(), b.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    return NAQS_OK;
+}
+
+template <int NW, int MODE>
+int launch_rows(naqs_table* t, const uint64_t* d_states, int64_t M, int64_t* d_counts, const int64_t* d_indptr,
+                uint64_t* d_col_keys, int64_t* d_col_ridx, double* d_vals, cudaStream_t stream) {
+    const size_t smem = tile_smem_bytes<NW>(t->tile_cap);
+    auto kern = rows_kernel<NW, MODE, kRowThreads>;
+    NAQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t blocks = (M + kRowThreads - 1) / kRowThreads;
+    kern<<<(unsigned)blocks, kRowThreads, smem, stream>>>(t->view(), t->d_tiles, t->n_tiles, t->tile_cap, t->sector, d_states,
+                                                         M, t->words, t->d_binom, d_counts, d_indptr, d_col_keys,
+                                                         d_col_ridx, d_vals);
+    NAQS_LAUNCHED();
+    return NAQS_OK;
+}
+
+template <int MODE>
+int dispatch_rows(naqs_table* t, const uint64_t* d_states, int64_t M, int64_t* d_counts, const int64_t* d_indptr,
+                  uint64_t* d_col_keys, int64_t* d_col_ridx, double* d_vals, cudaStream_t stream) {
+    switch (t->nw32) {
+        case 1: return launch_rows<1, MODE>(t, d_states, M, d_counts, d_indptr, d_col_keys, d_col_ridx, d_vals, stream);
+        case 2: return launch_rows<2, MODE>(t, d_states, M, d_counts, d_indptr, d_col_keys, d_col_ridx, d_vals, stream);
+        default: return launch_rows<4, MODE>(t, d_states, M, d_counts, d_indptr, d_col_keys, d_col_ridx, d_vals, stream);
+    }
+}
+
+template <int NW>
+__global__ void restricted_index_kernel(Sector sec, const uint64_t* __restrict__ keys, int64_t n,
+                                        const long long* __restrict__ binom, int64_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t j[NW];
+    load_key<NW>(keys, i, j);
+    out[i] = restricted_index<NW>(j, sec, binom);
+}
+
+}  // namespace
+
+extern "C" {
+
+int naqs_rows_count(naqs_table_t* t, const uint64_t* d_states, int64_t M, int64_t* d_counts, void* stream) {
+    NAQS_REQUIRE(t, NAQS_ERR_ARG, "naqs_rows_count: NULL table");
+    NAQS_REQUIRE(M >= 0 && (M == 0 || (d_states && d_counts)), NAQS_ERR_ARG, "naqs_rows_count: NULL buffers");
+    if (M == 0) return NAQS_OK;
+    DeviceGuard guard(t->device);
+    return dispatch_rows<kRowsCount>(t, d_states, M, d_counts, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int naqs_rows_fill(naqs_table_t* t, const uint64_t* d_states, int64_t M, const int64_t* d_indptr, uint64_t* d_col_keys,
+                   int64_t* d_col_ridx, double* d_vals, void* stream) {
+    NAQS_REQUIRE(t, NAQS_ERR_ARG, "naqs_rows_fill: NULL table");
+    NAQS_REQUIRE(M >= 0 && (M == 0 || (d_states && d_indptr && d_col_keys && d_vals)), NAQS_ERR_ARG, "naqs_rows_fill: NULL buffers");
+    if (M == 0) return NAQS_OK;
+    DeviceGuard guard(t->device);
+    if (d_col_ridx) { int rc = ensure_binom(t); if (rc) return rc; }
+    return dispatch_rows<kRowsFill>(t, d_states, M, nullptr, d_indptr, d_col_keys, d_col_ridx, d_vals, (cudaStream_t)stream);
+}
+
+int naqs_hij_dense(naqs_table_t* t, const uint64_t* d_states, int64_t M, double* d_hij, void* stream) {
+    NAQS_REQUIRE(t, NAQS_ERR_ARG, "naqs_hij_dense: NULL table");
+    NAQS_REQUIRE(M >= 0 && (M == 0 || (d_states && d_hij)), NAQS_ERR_ARG, "naqs_hij_dense: NULL buffers");
+    if (M == 0 || t->G == 0) return NAQS_OK;
+    DeviceGuard guard(t->device);
+    return dispatch_rows<kRowsDense>(t, d_states, M, nullptr, nullptr, nullptr, nullptr, d_hij, (cudaStream_t)stream);
+}
+
+int naqs_restricted_index(naqs_table_t* t, const uint64_t* d_keys, int64_t n, int64_t* d_out, void* stream) {
+    NAQS_REQUIRE(t, NAQS_ERR_ARG, "naqs_restricted_index: NULL table");
+    NAQS_REQUIRE(n >= 0 && (n == 0 || (d_keys && d_out)), NAQS_ERR_ARG, "naqs_restricted_index: NULL buffers");
+    if (n == 0) return NAQS_OK;
+    DeviceGuard guard(t->device);
+    int rc = ensure_binom(t);
+    if (rc) return rc;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (t->nw32) {
+        case 1: restricted_index_kernel<1><<<blocks, 256, 0, st>>>(t->sector, d_keys, n, t->d_binom, d_out); break;
+        case 2: restricted_index_kernel<2><<<blocks, 256, 0, st>>>(t->sector, d_keys, n, t->d_binom, d_out); break;
+        default: restricted_index_kernel<4><<<blocks, 256, 0, st>>>(t->sector, d_keys, n, t->d_binom, d_out); break;
+    }
+    NAQS_LAUNCHED();
+    return NAQS_OK;
+}
+
+int naqs_exclusive_scan(naqs_table_t* t, const int64_t* d_counts, int64_t n, int64_t* d_indptr, void* stream) {
+    NAQS_REQUIRE(t, NAQS_ERR_ARG, "naqs_exclusive_scan: NULL table");
+    NAQS_REQUIRE(n >= 0 && d_indptr && (n == 0 || d_counts), NAQS_ERR_ARG, "naqs_exclusive_scan: NULL buffers");
+    DeviceGuard guard(t->device);
+    return exclusive_scan_i64(t, d_counts, n, d_indptr, (cudaStream_t)stream);
+}
+
+int naqs_unique_keys(naqs_table_t* t, const uint64_t* d_keys, int64_t n, uint64_t* d_out, int64_t* h_n_unique, void* stream) {
+    NAQS_REQUIRE(t && h_n_unique, NAQS_ERR_ARG, "naqs_unique_keys: NULL argument");
+    NAQS_REQUIRE(n >= 0 && (n == 0 || (d_keys && d_out)), NAQS_ERR_ARG, "naqs_unique_keys: NULL buffers");
+    *h_n_unique = 0;
+    if (n == 0) return NAQS_OK;
+    DeviceGuard guard(t->device);
+    return sort_unique_keys(t, d_keys, n, d_out, h_n_unique, (cudaStream_t)stream);
+}
+
+}  // extern "C"

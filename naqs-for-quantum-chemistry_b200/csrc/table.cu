@@ -1,0 +1,336 @@
+// table.cu — table handle, amplitude lookup construction and the fused E_loc entry points.
+// C ABI documented in include/naqs_eloc.h.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "common.cuh"
+#include "eloc_kernels.cuh"
+
+namespace naqs {
+
+static thread_local std::string g_error;
+std::atomic<int64_t> g_launches{0};
+void set_error(const std::string& msg) { g_error = msg; }
+
+int ensure_ws(naqs_table* t, size_t bytes) {
+    if (bytes <= t->ws_bytes) return NAQS_OK;
+    if (t->d_ws) cudaFree(t->d_ws);
+    t->d_ws = nullptr; t->ws_bytes = 0;
+    size_t want = std::max(bytes, (size_t)1 << 20);
+    NAQS_CUDA(cudaMalloc(&t->d_ws, want));
+    t->ws_bytes = want;
+    return NAQS_OK;
+}
+
+// ------------------------------------------------------------------------------------------ lookup build
+__global__ void hash_init_kernel(HashSlot* slots, int64_t cap) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap) {
+        // one 32 B store per slot
+        ulonglong4 v = make_ulonglong4(kEmptyKey, kEmptyKey, 0ull, 0ull);
+        reinterpret_cast<ulonglong4*>(slots)[i] = v;
+    }
+}
+
+__device__ __forceinline__ ulonglong2 cas128(unsigned long long* addr, ulonglong2 cmp, ulonglong2 val) {
+    ulonglong2 old;
+    asm volatile(
+        "{\n .reg .b128 d, c, s;\n mov.b128 c, {%2, %3};\n mov.b128 s, {%4, %5};\n"
+        " atom.global.cas.b128 d, [%6], c, s;\n mov.b128 {%0, %1}, d;\n}"
+        : "=l"(old.x), "=l"(old.y)
+        : "l"(cmp.x), "l"(cmp.y), "l"(val.x), "l"(val.y), "l"(addr)
+        : "memory");
+    return old;
+}
+
+__global__ void hash_insert_kernel(HashSlot* slots, unsigned long long mask, const uint64_t* __restrict__ keys, int words,
+                                   const void* __restrict__ psi, int psi_dtype, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k0 = keys[i * words], k1 = words > 1 ? keys[i * words + 1] : 0ull;
+    const double2 p = load_psi(psi, psi_dtype, i);
+    unsigned long long h = hash_key(k0, k1) & mask;
+    while (true) {
+        HashSlot* sl = slots + h;
+        const ulonglong2 old = cas128(sl->key, make_ulonglong2(kEmptyKey, kEmptyKey), make_ulonglong2(k0, k1));
+        if ((old.x == kEmptyKey && old.y == kEmptyKey) || (old.x == k0 && old.y == k1)) {
+            // duplicates of a key are summed (scipy's H[idx[:,None], idx] repeats the column)
+            atomicAdd(&sl->re, p.x);
+            atomicAdd(&sl->im, p.y);
+            return;
+        }
+        h = (h + 1) & mask;
+    }
+}
+
+__global__ void dense_scatter_kernel(double2* dense, const uint64_t* __restrict__ keys, const void* __restrict__ psi,
+                                     int psi_dtype, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double2 p = load_psi(psi, psi_dtype, i);
+    double* dst = reinterpret_cast<double*>(dense + keys[i]);
+    atomicAdd(dst, p.x);
+    atomicAdd(dst + 1, p.y);
+}
+
+// ------------------------------------------------------------------------------------------ launch helpers
+constexpr int kThreads = 256;
+
+static int tile_cap_for(int nw32, int64_t K) {
+    // keep a tile <= ~56 KB so four CTAs of 256 threads fit one SM; whole table in one tile when it fits
+    const int per_term = 8 + 8 * nw32 + 4;
+    int cap = (56 * 1024 - 64) / per_term;
+    cap = std::max(cap, 256);
+    return (int)std::min<int64_t>(std::max<int64_t>(K, 1), cap);
+}
+
+}  // namespace naqs
+
+using namespace naqs;
+
+extern "C" {
+
+const char* naqs_last_error(void) { return g_error.c_str(); }
+int naqs_abi_version(void) { return NAQS_ABI_VERSION; }
+int naqs_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int64_t naqs_launch_count(void) { return g_launches.load(); }
+
+int naqs_table_create(naqs_table_t** out, const uint64_t* h_xy, const uint64_t* h_yz, const double* h_coeff,
+                      int64_t K, int words, int n_qubits, int n_alpha, int n_beta, int device) {
+    NAQS_REQUIRE(out != nullptr, NAQS_ERR_ARG, "naqs_table_create: out is NULL");
+    *out = nullptr;
+    NAQS_REQUIRE(K >= 0 && (K == 0 || (h_xy && h_yz && h_coeff)), NAQS_ERR_ARG, "naqs_table_create: NULL term arrays");
+    NAQS_REQUIRE(words == 1 || words == 2, NAQS_ERR_ARG, "naqs_table_create: words must be 1 or 2");
+    NAQS_REQUIRE(n_qubits >= 1 && n_qubits <= 64 * words - 1, NAQS_ERR_ARG,
+                 "naqs_table_create: n_qubits must be in [1, 63] (words=1) or [1, 127] (words=2)");
+    NAQS_REQUIRE(K < (1ll << 31), NAQS_ERR_ARG, "naqs_table_create: too many terms");
+    NAQS_REQUIRE((n_alpha < 0) == (n_beta < 0), NAQS_ERR_ARG, "naqs_table_create: give both n_alpha and n_beta or neither");
+    NAQS_REQUIRE(naqs_device_count() > device && device >= 0, NAQS_ERR_CUDA, "naqs_table_create: no such CUDA device (this library has no CPU fallback)");
+    DeviceGuard guard(device);
+    NAQS_REQUIRE(guard.ok, NAQS_ERR_CUDA, "naqs_table_create: cudaSetDevice failed");
+
+    auto* t = new naqs_table();
+    t->device = device; t->words = words; t->n_qubits = n_qubits; t->n_alpha = n_alpha; t->n_beta = n_beta; t->K = K;
+    t->nw32 = n_qubits <= 32 ? 1 : (n_qubits <= 64 ? 2 : 4);
+    const int NW = t->nw32;
+
+    // group by XY mask: ascending multi-word value (np.unique), stable in k
+    std::vector<int64_t> order(K);
+    std::iota(order.begin(), order.end(), 0);
+    auto key_less = [&](const uint64_t* a, const uint64_t* b) {
+        for (int w = words - 1; w >= 0; --w) if (a[w] != b[w]) return a[w] < b[w];
+        return false;
+    };
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return key_less(h_xy + a * words, h_xy + b * words); });
+    std::vector<uint32_t> yz((size_t)NW * std::max<int64_t>(K, 1)), gxy, gstart;
+    std::vector<double> coeff(std::max<int64_t>(K, 1));
+    std::vector<const uint64_t*> gkeys;
+    for (int64_t i = 0; i < K; ++i) {
+        const int64_t k = order[i];
+        if (i == 0 || std::memcmp(h_xy + k * words, h_xy + order[i - 1] * words, 8 * words) != 0) {
+            gstart.push_back((uint32_t)i);
+            gkeys.push_back(h_xy + k * words);
+        }
+        for (int w = 0; w < NW; ++w) yz[(size_t)w * K + i] = (uint32_t)(h_yz[k * words + w / 2] >> (32 * (w % 2)));
+        coeff[i] = h_coeff[k];
+    }
+    const int64_t G = (int64_t)gstart.size();
+    gstart.push_back((uint32_t)K);
+    gxy.resize((size_t)NW * std::max<int64_t>(G, 1));
+    for (int64_t g = 0; g < G; ++g)
+        for (int w = 0; w < NW; ++w) gxy[(size_t)w * G + g] = (uint32_t)(gkeys[g][w / 2] >> (32 * (w % 2)));
+    t->G = G;
+    {   // Kyz for naqs_table_info
+        std::vector<int64_t> o2(K);
+        std::iota(o2.begin(), o2.end(), 0);
+        std::sort(o2.begin(), o2.end(), [&](int64_t a, int64_t b) { return key_less(h_yz + a * words, h_yz + b * words); });
+        int64_t n = 0;
+        for (int64_t i = 0; i < K; ++i)
+            if (i == 0 || std::memcmp(h_yz + o2[i] * words, h_yz + o2[i - 1] * words, 8 * words) != 0) ++n;
+        t->Kyz = n;
+    }
+    // sector masks
+    Sector& sec = t->sector;
+    std::memset(&sec, 0, sizeof(sec));
+    sec.enabled = n_alpha >= 0; sec.n_alpha = n_alpha; sec.n_beta = n_beta; sec.n_qubits = n_qubits;
+    for (int q = 0; q < n_qubits; ++q) ((q % 2 == 0) ? sec.even : sec.odd)[q / 32] |= 1u << (q % 32);
+
+    // tiles
+    t->tile_cap = tile_cap_for(NW, K);
+    std::vector<Tile> tiles;
+    for (int64_t t0 = 0; t0 < K; t0 += t->tile_cap) {
+        Tile tl;
+        tl.t0 = (uint32_t)t0; tl.t1 = (uint32_t)std::min<int64_t>(K, t0 + t->tile_cap);
+        // first group with gstart[g+1] > t0 ; one past the last group with gstart[g] < t1
+        tl.g0 = (uint32_t)(std::upper_bound(gstart.begin(), gstart.end(), tl.t0) - gstart.begin() - 1);
+        tl.g1 = (uint32_t)(std::lower_bound(gstart.begin(), gstart.end(), tl.t1) - gstart.begin());
+        tiles.push_back(tl);
+    }
+    t->n_tiles = (int)tiles.size();
+
+    int rc = NAQS_OK;
+    auto upload = [&](void** dptr, const void* src, size_t bytes) -> int {
+        NAQS_CUDA(cudaMalloc(dptr, std::max<size_t>(bytes, 16)));
+        if (bytes) NAQS_CUDA(cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice));
+        return NAQS_OK;
+    };
+    if ((rc = upload((void**)&t->d_yz, yz.data(), (size_t)NW * K * 4)) ||
+        (rc = upload((void**)&t->d_coeff, coeff.data(), (size_t)K * 8)) ||
+        (rc = upload((void**)&t->d_gxy, gxy.data(), (size_t)NW * G * 4)) ||
+        (rc = upload((void**)&t->d_gstart, gstart.data(), (size_t)(G + 1) * 4)) ||
+        (rc = upload((void**)&t->d_tiles, tiles.data(), tiles.size() * sizeof(Tile)))) {
+        naqs_table_destroy(t);
+        return rc;
+    }
+    if (cudaStreamCreateWithFlags(&t->own_stream, cudaStreamNonBlocking) != cudaSuccess) t->own_stream = nullptr;
+    *out = t;
+    return NAQS_OK;
+}
+
+int naqs_table_destroy(naqs_table_t* t) {
+    if (!t) return NAQS_OK;
+    DeviceGuard guard(t->device);
+    cudaFree(t->d_yz); cudaFree(t->d_coeff); cudaFree(t->d_gxy); cudaFree(t->d_gstart);
+    cudaFree(t->d_dense); cudaFree(t->d_slots); cudaFree(t->d_ws); cudaFree(t->d_stage);
+    if (t->h_pinned) cudaFreeHost(t->h_pinned);
+    if (t->own_stream) cudaStreamDestroy(t->own_stream);
+    cudaFree(t->d_tiles); cudaFree(t->d_binom);
+    delete t;
+    return NAQS_OK;
+}
+
+int naqs_table_info(const naqs_table_t* t, int64_t* info) {
+    NAQS_REQUIRE(t && info, NAQS_ERR_ARG, "naqs_table_info: NULL argument");
+    info[0] = t->K; info[1] = t->G; info[2] = t->Kyz; info[3] = t->words;
+    info[4] = t->n_qubits; info[5] = t->n_alpha; info[6] = t->n_beta; info[7] = t->device;
+    return NAQS_OK;
+}
+
+int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi, int psi_dtype, int64_t n, int kind,
+                      void* stream_) {
+    NAQS_REQUIRE(t, NAQS_ERR_ARG, "naqs_lookup_build: NULL table");
+    NAQS_REQUIRE(n >= 0 && (n == 0 || (d_keys && d_psi)), NAQS_ERR_ARG, "naqs_lookup_build: NULL keys/psi");
+    NAQS_REQUIRE(psi_dtype == NAQS_C128 || psi_dtype == NAQS_C64, NAQS_ERR_DTYPE, "naqs_lookup_build: psi must be complex64 or complex128");
+    DeviceGuard guard(t->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (kind == NAQS_LOOKUP_AUTO) kind = (t->n_qubits <= 22) ? NAQS_LOOKUP_DENSE : NAQS_LOOKUP_HASH;
+    NAQS_REQUIRE(kind == NAQS_LOOKUP_DENSE || kind == NAQS_LOOKUP_HASH, NAQS_ERR_ARG, "naqs_lookup_build: bad kind");
+    const int blocks = (int)((n + 255) / 256);
+    if (kind == NAQS_LOOKUP_DENSE) {
+        NAQS_REQUIRE(t->n_qubits <= 30, NAQS_ERR_ARG, "naqs_lookup_build: dense lookup needs n_qubits <= 30");
+        const int64_t entries = 1ll << t->n_qubits;
+        if (t->dense_entries < entries) {
+            cudaFree(t->d_dense); t->d_dense = nullptr; t->dense_entries = 0;
+            NAQS_CUDA(cudaMalloc((void**)&t->d_dense, (size_t)entries * sizeof(double2)));
+            t->dense_entries = entries;
+        }
+        NAQS_CUDA(cudaMemsetAsync(t->d_dense, 0, (size_t)entries * sizeof(double2), stream));
+        if (n > 0) {
+            dense_scatter_kernel<<<blocks, 256, 0, stream>>>(t->d_dense, d_keys, d_psi, psi_dtype, n);
+            NAQS_LAUNCHED();
+        }
+    } else {
+        int64_t cap = 1024;
+        while (cap < 2 * n) cap <<= 1;
+        if (t->hash_alloc < cap) {
+            cudaFree(t->d_slots); t->d_slots = nullptr; t->hash_alloc = 0;
+            NAQS_CUDA(cudaMalloc((void**)&t->d_slots, (size_t)cap * sizeof(HashSlot)));
+            t->hash_alloc = cap;
+        }
+        t->hash_cap = cap;
+        hash_init_kernel<<<(int)((cap + 255) / 256), 256, 0, stream>>>(t->d_slots, cap);
+        NAQS_LAUNCHED();
+        if (n > 0) {
+            hash_insert_kernel<<<blocks, 256, 0, stream>>>(t->d_slots, (unsigned long long)(cap - 1), d_keys, t->words,
+                                                           d_psi, psi_dtype, n);
+            NAQS_LAUNCHED();
+        }
+    }
+    t->lookup_kind = kind;
+    t->lookup_n = n;
+    return NAQS_OK;
+}
+
+}  // extern "C"
+
+template <int NW>
+static int launch_eloc(naqs_table_t* t, const uint64_t* d_states, const void* d_psi, int psi_dtype, int64_t M,
+                       double* d_eloc, cudaStream_t stream) {
+    constexpr int R = 4;
+    const size_t smem = tile_smem_bytes<NW>(t->tile_cap);
+    auto kern = eloc_direct_kernel<NW, R, kThreads>;
+    NAQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t per_block = (int64_t)kThreads * R;
+    const int64_t blocks = (M + per_block - 1) / per_block;
+    kern<<<(unsigned)blocks, kThreads, smem, stream>>>(t->view(), t->d_tiles, t->n_tiles, t->tile_cap,
+                                                      t->sector, t->lookup(), d_states, d_psi, psi_dtype, M,
+                                                      reinterpret_cast<double2*>(d_eloc));
+    NAQS_LAUNCHED();
+    return NAQS_OK;
+}
+
+extern "C" {
+
+int naqs_eloc(naqs_table_t* t, const uint64_t* d_states, const void* d_psi, int psi_dtype, int64_t M, double* d_eloc,
+              void* stream_) {
+    NAQS_REQUIRE(t, NAQS_ERR_ARG, "naqs_eloc: NULL table");
+    NAQS_REQUIRE(M >= 0 && (M == 0 || (d_states && d_psi && d_eloc)), NAQS_ERR_ARG, "naqs_eloc: NULL buffers");
+    NAQS_REQUIRE(psi_dtype == NAQS_C128 || psi_dtype == NAQS_C64, NAQS_ERR_DTYPE, "naqs_eloc: psi must be complex64 or complex128");
+    NAQS_REQUIRE(t->lookup_kind != 0, NAQS_ERR_STATE, "naqs_eloc: call naqs_lookup_build first");
+    NAQS_REQUIRE(M < (1ll << 40), NAQS_ERR_ARG, "naqs_eloc: batch too large");
+    if (M == 0) return NAQS_OK;
+    DeviceGuard guard(t->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    switch (t->nw32) {
+        case 1: return launch_eloc<1>(t, d_states, d_psi, psi_dtype, M, d_eloc, stream);
+        case 2: return launch_eloc<2>(t, d_states, d_psi, psi_dtype, M, d_eloc, stream);
+        default: return launch_eloc<4>(t, d_states, d_psi, psi_dtype, M, d_eloc, stream);
+    }
+}
+
+int naqs_eloc_host(naqs_table_t* t, const uint64_t* h_states, const void* h_psi, int psi_dtype, int64_t M,
+                   const uint64_t* h_tkeys, const void* h_tpsi, int64_t T, double* h_eloc) {
+    NAQS_REQUIRE(t, NAQS_ERR_ARG, "naqs_eloc_host: NULL table");
+    NAQS_REQUIRE(M >= 0 && (M == 0 || (h_states && h_psi && h_eloc)), NAQS_ERR_ARG, "naqs_eloc_host: NULL buffers");
+    NAQS_REQUIRE(psi_dtype == NAQS_C128 || psi_dtype == NAQS_C64, NAQS_ERR_DTYPE, "naqs_eloc_host: psi must be complex64 or complex128");
+    if (M == 0) return NAQS_OK;
+    DeviceGuard guard(t->device);
+    const size_t psz = psi_dtype == NAQS_C64 ? 8 : 16;
+    const size_t kb = (size_t)8 * t->words;
+    const bool own_table = h_tkeys != nullptr;
+    if (!own_table) T = M;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_states = 0, o_psi = al(M * kb), o_tk = o_psi + al(M * psz), o_tp = o_tk + (own_table ? al(T * kb) : 0),
+                 o_out = o_tp + (own_table ? al(T * psz) : 0), total = o_out + al((size_t)M * 16);
+    if (t->stage_bytes < total) {
+        cudaFree(t->d_stage); t->d_stage = nullptr; t->stage_bytes = 0;
+        NAQS_CUDA(cudaMalloc(&t->d_stage, total));
+        t->stage_bytes = total;
+    }
+    char* d = (char*)t->d_stage;
+    cudaStream_t st = t->own_stream;
+    NAQS_CUDA(cudaMemcpyAsync(d + o_states, h_states, M * kb, cudaMemcpyHostToDevice, st));
+    NAQS_CUDA(cudaMemcpyAsync(d + o_psi, h_psi, M * psz, cudaMemcpyHostToDevice, st));
+    const uint64_t* d_tk = (const uint64_t*)(d + o_states);
+    const void* d_tp = d + o_psi;
+    if (own_table) {
+        NAQS_CUDA(cudaMemcpyAsync(d + o_tk, h_tkeys, T * kb, cudaMemcpyHostToDevice, st));
+        NAQS_CUDA(cudaMemcpyAsync(d + o_tp, h_tpsi, T * psz, cudaMemcpyHostToDevice, st));
+        d_tk = (const uint64_t*)(d + o_tk); d_tp = d + o_tp;
+    }
+    int rc = naqs_lookup_build(t, d_tk, d_tp, psi_dtype, T, NAQS_LOOKUP_AUTO, st);
+    if (rc) return rc;
+    rc = naqs_eloc(t, (const uint64_t*)(d + o_states), d + o_psi, psi_dtype, M, (double*)(d + o_out), st);
+    if (rc) return rc;
+    NAQS_CUDA(cudaMemcpyAsync(h_eloc, d + o_out, (size_t)M * 16, cudaMemcpyDeviceToHost, st));
+    NAQS_CUDA(cudaStreamSynchronize(st));
+    return NAQS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,192 @@
+"""PauliHamiltonian — B200-backed mirror of src/optimizer/hamiltonian.py.
+
+`PauliHamiltonian.get(hilbert, qubit_hamiltonian, ...)` keeps the reference's signature and returns
+an object with the reference's methods (update_H / get_H / get_restricted_H / get_coupled_state_idxs /
+freeze_H / unfreeze_H / is_frozen / save / load), so src/optimizer/energy.py runs unchanged on top of it.
+Rows are produced by the CUDA rows kernels (naqs_rows_count / naqs_rows_fill) instead of the numpy
+broadcast + popcount_parity + get_Hij_cy pipeline; the scipy CSR cache semantics are kept.
+
+New, and what `calculate_local_energy` should call: `local_energy(states_idx, psi)` — the fused,
+stateless device path (no H cache, no M x Kyz / M x Kxy intermediates).
+"""
+import os
+
+import numpy as np
+import torch
+from scipy.sparse import csr_matrix, load_npz, save_npz
+
+from . import _lib
+from .hilbert import Encoding
+from .pauli import pack_terms
+from .table import DeviceTermTable
+
+
+class PauliHamiltonian:
+
+    @staticmethod
+    def _format_fnames(fname, fname_H=None):
+        f, ext = os.path.splitext(fname)
+        if f[-5:] != "_info":
+            fbase, fname = f, f"{f}_info"
+        else:
+            fbase, fname = f[:-5], f
+        return f"{fname}.npz", f"{fbase}.npz"
+
+    @staticmethod
+    def get(hilbert, qubit_hamiltonian, hamiltonian_fname=None, restricted_idxs=None, n_excitations_max=None,
+            verbose=False, dtype=np.float32, device=None):
+        """Same arguments as the reference's factory (hamiltonian.py:48-62).  A saved Hamiltonian
+        (`*_info.npz` + `.npz`) is loaded into the cache exactly like the reference does."""
+        ph = PauliHamiltonianB200(hilbert, qubit_hamiltonian, restricted_idxs, n_excitations_max, verbose, dtype, device)
+        if hamiltonian_fname is not None:
+            info_name, npz_name = PauliHamiltonian._format_fnames(hamiltonian_fname)
+            if os.path.exists(info_name):
+                ph.load(info_name)
+            elif os.path.exists(npz_name):
+                ph.load_H(npz_name)
+                ph.freeze_H()
+        return ph
+
+
+class PauliHamiltonianB200:
+    def __init__(self, hilbert, qubit_hamiltonian, restricted_idxs=None, n_excitations_max=None, verbose=False,
+                 dtype=np.float32, device=None):
+        self.hilbert = hilbert
+        assert self.hilbert.encoding.name == Encoding.SIGNED.name, "PauliCouplings requires Encoding.SIGNED."
+        self.qubit_hamiltonian = qubit_hamiltonian
+        self.restricted_idxs = self.hilbert.full2restricted_idx(restricted_idxs)
+        self.n_excitations_max = n_excitations_max
+        self.dtype = dtype
+        self.verbose = verbose
+
+        N = self.hilbert.N
+        n_alpha, n_beta = getattr(hilbert, "N_alpha", None), getattr(hilbert, "N_beta", None)
+        if n_alpha is not None and np.ndim(n_alpha) > 0:
+            raise NotImplementedError("partially restricted Hilbert spaces (several (N_alpha, N_beta) sectors) are not supported on the device path")
+        xy, yz, c = pack_terms(qubit_hamiltonian.terms, N, n_occ=getattr(hilbert, "N_occ", 0) or 0,
+                               n_excitations_max=n_excitations_max)
+        # reference attributes (hamiltonian.py:246-252)
+        idt = self.hilbert.get_idx_dtype("np") if hasattr(self.hilbert, "get_idx_dtype") else np.int64
+        self.XY_sites_idx = xy[:, 0].view(np.int64).astype(idt)
+        self.YZ_sites_idx = yz[:, 0].view(np.int64).astype(idt)
+        self.couplings = c.astype(dtype).reshape(-1, 1)
+        self._unique_XY_sites_idx, self._unique2all_XY_sites_idx = np.unique(self.XY_sites_idx, return_inverse=True)
+        self._unique_YZ_sites_idx, self._unique2all_YZ_sites_idx = np.unique(self.YZ_sites_idx, return_inverse=True)
+        # the device accumulates in float64 with the coefficients the reference would hold in `dtype`
+        self.table = DeviceTermTable(xy, yz, self.couplings.reshape(-1).astype(np.float64), N, n_alpha, n_beta, device)
+
+        d = self.hilbert.size
+        self.H = csr_matrix(([], ([], [])), shape=(d, d), dtype=self.dtype)
+        self._cached_idxs = np.array([], dtype=idt)
+        self._frozen_H = False
+        self._restricted_H = None
+        if verbose:
+            print(f"Pauli Hamiltonian has K={self.table.K} terms, {self.table.Kxy} unique XY masks, {self.table.Kyz} unique YZ masks "
+                  f"(device {self.table.device}).")
+
+    # ------------------------------------------------------------------ fused path
+    def local_energy(self, states_idx, psi, ret_numpy=True):
+        """E_loc (complex128) of the sampled batch, only couplings inside the batch contribute
+        (energy.py:247-248).  Stateless: nothing is cached."""
+        out = self.table.local_energy(np.asarray(states_idx).reshape(-1) if not torch.is_tensor(states_idx) else states_idx.reshape(-1), psi)
+        return _lib.complex_from_pairs(out) if ret_numpy else out
+
+    # ------------------------------------------------------------------ reference API
+    def _rows_csr(self, state_i_idx):
+        indptr, cols, ridx, vals = self.table.rows(state_i_idx.astype(np.int64), with_restricted_index=True)
+        indptr, ridx, vals = indptr.cpu().numpy(), ridx.cpu().numpy(), vals.cpu().numpy()
+        i_idx = np.asarray(self.hilbert.full2restricted_idx(state_i_idx)).astype(np.int64)
+        rows = np.repeat(i_idx, np.diff(indptr))
+        return csr_matrix((vals.astype(self.dtype), (rows, ridx)), shape=(self.hilbert.size, self.hilbert.size))
+
+    def update_H(self, state_idx, check_unseen=True, assume_unique=False):
+        """hamiltonian.py:272-370: add the rows of not-yet-cached states to the sparse H and return it."""
+        if not self._frozen_H:
+            state_i_idx = self.hilbert.to_idx_array(state_idx).reshape(-1)
+            if check_unseen:
+                state_i_idx = np.setdiff1d(state_i_idx, self._cached_idxs, assume_unique=assume_unique)
+                if len(state_i_idx) == 0:
+                    return self.get_H()
+            H_new = self._rows_csr(state_i_idx)
+            self._cached_idxs = np.concatenate((self._cached_idxs, state_i_idx))
+            self.H = self.H + H_new
+        return self.H
+
+    def __get_new_H_subspace(self, idxs):
+        idxs = np.asarray(idxs).reshape(-1)
+        return self.H[idxs[:, np.newaxis], idxs]
+
+    def get_H(self, idxs=None):
+        """hamiltonian.py:96-111.  (The reference's full-sector shortcut returns rows in restricted order even
+        when `idxs` is permuted — quirk q1 of SURVEY.md §8a; here the caller's order is always kept.)"""
+        if idxs is not None:
+            idxs = self.hilbert.full2restricted_idx(idxs.detach().cpu().numpy() if torch.is_tensor(idxs) else idxs)
+            return self.__get_new_H_subspace(idxs)
+        return self.H
+
+    def get_restricted_H(self):
+        if self._frozen_H and (self._restricted_H is not None):
+            return self._restricted_H
+        r = self.restricted_idxs
+        H = self.__get_new_H_subspace(r.detach().cpu().numpy() if torch.is_tensor(r) else r)
+        if self._frozen_H:
+            self._restricted_H = H
+        return H
+
+    def get_coupled_state_idxs(self, state_idxs, return_unique=False):
+        """hamiltonian.py:122-132 (rows of the cached H, i.e. restricted indices)."""
+        coupled = [self.H.indices[self.H.indptr[i]:self.H.indptr[i + 1]] for i in state_idxs]
+        if return_unique:
+            coupled = np.unique(np.concatenate(coupled))
+        return coupled
+
+    def coupled_state_set(self, states_idx):
+        """Device version of get_coupled_state_idxs(return_unique=True) for FULL state indices, without the cache:
+        sorted unique coupled keys (radix sort + unique on the GPU)."""
+        keys = self.table.coupled_state_set(np.asarray(states_idx).reshape(-1))
+        return keys[:, 0].cpu().numpy()
+
+    def freeze_H(self):
+        self._frozen_H = True
+
+    def unfreeze_H(self):
+        self._frozen_H = False
+        self._restricted_H = None
+
+    def is_frozen(self):
+        return self._frozen_H
+
+    # ------------------------------------------------------------------ npz persistence (hamiltonian.py:146-198)
+    def load_H(self, fname):
+        if os.path.splitext(fname)[-1] != ".npz":
+            fname += ".npz"
+        self.H = load_npz(fname)
+
+    def save_H(self, fname):
+        if os.path.splitext(fname)[-1] != ".npz":
+            fname += ".npz"
+        d = os.path.dirname(fname)
+        if d:
+            os.makedirs(d, exist_ok=True)
+        data = self.H.data
+        data[np.abs(self.H.data) < 1e-12] = 0
+        self.H.data = data
+        self.H.eliminate_zeros()
+        save_npz(fname, self.H)
+
+    def load(self, fname, fname_H=None):
+        fname, fname_H = PauliHamiltonian._format_fnames(fname, fname_H)
+        with np.load(fname, allow_pickle=True) as f_in:
+            info = f_in["info"]
+        self._cached_idxs = info[0]
+        self._frozen_H = info[1]
+        self.load_H(fname_H)
+
+    def save(self, fname, fname_H=None):
+        fname, fname_H = PauliHamiltonian._format_fnames(fname, fname_H)
+        d = os.path.dirname(fname)
+        if d:
+            os.makedirs(d, exist_ok=True)
+        info = np.array([self._cached_idxs, self._frozen_H, fname_H], dtype=object)
+        np.savez(fname, info=info)
+        self.save_H(fname_H)

@@ -1,0 +1,180 @@
+"""DeviceTermTable — Python owner of a device-resident Pauli term table (naqs_table_t).
+
+The fused Level-1 entry (`local_energy`) is what `calculate_local_energy` calls; `rows`,
+`hij_dense`, `coupled_state_set`, `restricted_index` and `stats` expose the other C-ABI entries.
+Semantics follow the reference exactly (see include/naqs_eloc.h for file:line citations).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import LOOKUP_AUTO, LOOKUP_DENSE, LOOKUP_HASH  # noqa: F401
+
+
+class DeviceTermTable:
+    def __init__(self, xy, yz, coeff, n_qubits, n_alpha=None, n_beta=None, device=None):
+        """xy, yz: packed masks in REFERENCE TERM ORDER (ints, integer arrays or [K, words] uint64);
+        coeff: float64 [K] (src/optimizer/hamiltonian.py:373-430).  n_alpha=None => no sector filter."""
+        self.device = _lib.require_cuda(device)
+        self.n_qubits = int(n_qubits)
+        self.words = _lib.n_words(self.n_qubits)
+        self.n_alpha = None if n_alpha is None else int(n_alpha)
+        self.n_beta = None if n_beta is None else int(n_beta)
+        xy = _lib.keys_to_numpy(xy, self.words)
+        yz = _lib.keys_to_numpy(yz, self.words)
+        c = np.ascontiguousarray(np.asarray(coeff).reshape(-1), np.float64)
+        if not (len(xy) == len(yz) == len(c)):
+            raise ValueError("xy, yz and coeff must have the same length")
+        self._h = C.c_void_p()
+        lib = _lib.load()
+        _lib.check(lib.naqs_table_create(C.byref(self._h), _lib.ptr(xy), _lib.ptr(yz), _lib.ptr(c), len(c), self.words,
+                                         self.n_qubits, -1 if n_alpha is None else self.n_alpha,
+                                         -1 if n_beta is None else self.n_beta, self.device.index), "naqs_table_create")
+        info = np.zeros(8, np.int64)
+        _lib.check(lib.naqs_table_info(self._h, _lib.ptr(info)))
+        self.K, self.Kxy, self.Kyz = int(info[0]), int(info[1]), int(info[2])
+        self._lookup_built = False
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.load().naqs_table_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _keys(self, x):
+        return _lib.keys_to_device(x, self.words, self.device)
+
+    def _stream(self):
+        return _lib.stream_ptr(self.device)
+
+    # ------------------------------------------------------------------ amplitude lookup
+    def build_lookup(self, keys, psi, kind=LOOKUP_AUTO):
+        """(key, psi) pairs of the sampled batch -> device lookup structure (duplicates summed)."""
+        k = self._keys(keys)
+        p, code = _lib.psi_to_device(psi, self.device)
+        if p.shape[0] != k.shape[0]:
+            raise ValueError("keys and psi must have the same length")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().naqs_lookup_build(self._h, _lib.ptr(k), _lib.ptr(p), code, k.shape[0], kind, self._stream()),
+                       "naqs_lookup_build")
+        self._lookup_built = True
+        return self
+
+    # ------------------------------------------------------------------ fused E_loc (Level-1)
+    def local_energy(self, states, psi, table_keys=None, table_psi=None, kind=LOOKUP_AUTO, out=None, rebuild_lookup=True):
+        """E_loc of every state in `states` (src/optimizer/energy.py:245-248), complex128.
+
+        states/psi on the host (numpy / CPU tensors) or on the device (CUDA tensors).  The lookup table is
+        the batch itself unless (table_keys, table_psi) are given.  Returns a CUDA float64 tensor [M, 2]
+        (re, im) — use `_lib.complex_from_pairs` / `.cpu()` to bring it back."""
+        k = self._keys(states)
+        p, code = _lib.psi_to_device(psi, self.device)
+        M = k.shape[0]
+        if p.shape[0] != M:
+            raise ValueError("states and psi must have the same length")
+        if rebuild_lookup or not self._lookup_built:
+            if table_keys is None:
+                self.build_lookup(k, torch.view_as_complex(p), kind)
+            else:
+                self.build_lookup(table_keys, table_psi, kind)
+        if out is None:
+            out = torch.empty((M, 2), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().naqs_eloc(self._h, _lib.ptr(k), _lib.ptr(p), code, M, _lib.ptr(out), self._stream()), "naqs_eloc")
+        return out
+
+    def local_energy_host(self, states, psi, table_keys=None, table_psi=None):
+        """Host-buffer path (numpy in, numpy complex128 out) through naqs_eloc_host: pinned-free
+        synchronous upload -> lookup build -> fused kernel -> download."""
+        k = _lib.keys_to_numpy(states, self.words)
+        p = np.ascontiguousarray(psi)
+        if p.dtype not in (np.complex64, np.complex128):
+            p = p.astype(np.complex128)
+        code = _lib.NAQS_C64 if p.dtype == np.complex64 else _lib.NAQS_C128
+        out = np.empty(len(k), np.complex128)
+        tk = tp = None
+        T = 0
+        if table_keys is not None:
+            tk = _lib.keys_to_numpy(table_keys, self.words)
+            tp = np.ascontiguousarray(table_psi).astype(p.dtype)
+            T = len(tk)
+        _lib.check(_lib.load().naqs_eloc_host(self._h, _lib.ptr(k), _lib.ptr(p), code, len(k), _lib.ptr(tk), _lib.ptr(tp), T,
+                                              _lib.ptr(out)), "naqs_eloc_host")
+        return out
+
+    # ------------------------------------------------------------------ stored rows (CSR / coupled sets)
+    def rows(self, states, with_restricted_index=True):
+        """Stored couplings of each state (src/optimizer/hamiltonian.py:301-363):
+        -> (indptr [M+1] int64, col_keys [nnz, words] int64 bit patterns, col_ridx [nnz] int64 or None, vals [nnz] float64),
+        all CUDA tensors; columns in ascending unique-XY order."""
+        lib = _lib.load()
+        k = self._keys(states)
+        M = k.shape[0]
+        counts = torch.empty(M, dtype=torch.int64, device=self.device)
+        indptr = torch.empty(M + 1, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            st = self._stream()
+            _lib.check(lib.naqs_rows_count(self._h, _lib.ptr(k), M, _lib.ptr(counts), st), "naqs_rows_count")
+            _lib.check(lib.naqs_exclusive_scan(self._h, _lib.ptr(counts), M, _lib.ptr(indptr), st), "naqs_exclusive_scan")
+            nnz = int(indptr[-1].item())
+            cols = torch.empty((nnz, self.words), dtype=torch.int64, device=self.device)
+            ridx = torch.empty(nnz, dtype=torch.int64, device=self.device) if with_restricted_index else None
+            vals = torch.empty(nnz, dtype=torch.float64, device=self.device)
+            _lib.check(lib.naqs_rows_fill(self._h, _lib.ptr(k), M, _lib.ptr(indptr), _lib.ptr(cols), _lib.ptr(ridx), _lib.ptr(vals), st),
+                       "naqs_rows_fill")
+        return indptr, cols, ridx, vals
+
+    def hij_dense(self, states):
+        """[M, Kxy] float64: exactly get_Hij_cy's output (src_cpp/hamiltonian_math.pyx:200-288)."""
+        k = self._keys(states)
+        out = torch.empty((k.shape[0], self.Kxy), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().naqs_hij_dense(self._h, _lib.ptr(k), k.shape[0], _lib.ptr(out), self._stream()), "naqs_hij_dense")
+        return out
+
+    def unique_keys(self, keys):
+        """Sorted unique keys (device radix sort + adjacent unique): [U, words] int64 bit patterns."""
+        k = self._keys(keys)
+        out = torch.empty_like(k)
+        n_unique = C.c_int64(0)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().naqs_unique_keys(self._h, _lib.ptr(k), k.shape[0], _lib.ptr(out), C.byref(n_unique), self._stream()),
+                       "naqs_unique_keys")
+        return out[: n_unique.value]
+
+    def coupled_state_set(self, states):
+        """get_coupled_state_idxs(return_unique=True) (src/optimizer/hamiltonian.py:122-132), as keys."""
+        _, cols, _, _ = self.rows(states, with_restricted_index=False)
+        return self.unique_keys(cols)
+
+    def restricted_index(self, keys):
+        """full2restricted_idx (src/utils/hilbert.py:607-640) by combinatorial ranking: int64 [n], -1 outside the sector."""
+        k = self._keys(keys)
+        out = torch.empty(k.shape[0], dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().naqs_restricted_index(self._h, _lib.ptr(k), k.shape[0], _lib.ptr(out), self._stream()),
+                       "naqs_restricted_index")
+        return out
+
+    def stats(self, eloc, weights=None):
+        """[sum w, sum w Re E, sum w Im E, sum w (Re E)^2, n] in fp64 (src/optimizer/energy.py:328,372-375)."""
+        e = eloc if torch.is_tensor(eloc) else torch.from_numpy(np.ascontiguousarray(eloc))
+        if e.is_complex():
+            e = torch.view_as_real(e.to(torch.complex128))
+        e = e.to(self.device, torch.float64).contiguous()
+        w = None
+        if weights is not None:
+            w = (weights if torch.is_tensor(weights) else torch.from_numpy(np.asarray(weights))).to(self.device, torch.float64).reshape(-1).contiguous()
+        out = torch.empty(5, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().naqs_eloc_stats(self._h, _lib.ptr(e), _lib.ptr(w), e.shape[0], _lib.ptr(out), self._stream()),
+                       "naqs_eloc_stats")
+        return out

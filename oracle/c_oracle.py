@@ -59,7 +59,7 @@ class COracleTable:
     """Term table handle of the C oracle (n_alpha=None => no sector filter)."""
 
     def __init__(self, xy, yz, coeff, n_qubits, n_alpha=None, n_beta=None):
-        self.W = 1 if n_qubits <= 64 else 2
+        self.W = 1 if n_qubits <= 63 else 2
         self.n_qubits = n_qubits
         xy, yz = _keys(xy, self.W), _keys(yz, self.W)
         c = np.ascontiguousarray(coeff, np.float64).reshape(-1)

@@ -38,7 +38,7 @@ U64 = np.uint64
 
 # --------------------------------------------------------------------------- keys
 def n_words(n_qubits):
-    return 1 if n_qubits <= 64 else 2
+    return 1 if n_qubits <= 63 else 2
 
 
 def as_keys(x, W=1):

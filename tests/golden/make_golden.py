@@ -16,6 +16,7 @@ Files:
   eloc_<case>.npz         seeded batches: states, psi (complex64), eloc (complex128) from
                           energy.py:245-248; for small cases also the stored CSR rows of H
   level0.npz              input/output pairs of the five Cython entry points
+  terms_<mol>.json        the raw Pauli strings of H2 / LiH (inputs for the pack_terms tests; the pickles cannot travel)
 """
 import json
 import os
@@ -169,8 +170,18 @@ def make_level0():
     print("level0 done")
 
 
+def make_terms_json():
+    for mol in ("H2", "LiH"):
+        terms = rh.load_terms(mol)
+        out = [[[[int(q), p] for q, p in t], float(c.real), float(c.imag)] for t, c in terms.items()]
+        with open(os.path.join(OUT, f"terms_{mol}.json"), "w") as f:
+            json.dump(out, f)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["tables", "known", "eloc", "level0"]
+    which = sys.argv[1:] or ["tables", "known", "eloc", "level0", "terms"]
+    if "terms" in which:
+        make_terms_json()
     if "tables" in which:
         make_tables()
     if "known" in which:

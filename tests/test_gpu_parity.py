@@ -1,0 +1,394 @@
+"""Parity tests proper (run on the B200 with -m gpu): the CUDA path, called through the C ABI
+(ctypes -> libnaqs_eloc.so), against the golden fixtures and the oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): coupled-state sets, matrix elements and signs BIT-EXACT;
+fp64 E_loc within 1e-12 relative."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+from conftest import CASE_TABLE, GOLDEN, case_sector, load_case, load_table, random_sector_states
+
+pytestmark = pytest.mark.gpu
+
+ELOC_RTOL = 1e-12  # north_star: "fp64 E_loc within 1e-12 relative"
+
+
+def _mods():
+    import naqs_b200
+    from oracle import c_oracle
+    from oracle import eloc_oracle as eo
+    return naqs_b200, c_oracle, eo
+
+
+def random_keys(N, m, seed):
+    """m distinct uniformly random keys below 2^N (N <= 62)."""
+    rng = np.random.default_rng(seed)
+    if 2 ** N <= 4 * m:
+        return rng.choice(2 ** N, m, replace=False).astype(np.uint64)
+    out = np.unique(rng.integers(0, 2 ** N, size=2 * m, dtype=np.int64))
+    return rng.permutation(out)[:m].astype(np.uint64)
+
+
+def rel_err(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def gpu_eloc(table, states, psi, **kw):
+    import naqs_b200
+    out = table.local_energy(states, psi, **kw)
+    return naqs_b200._lib.complex_from_pairs(out)
+
+
+def make_tables(mol, sector=True):
+    nb200, c_oracle, _ = _mods()
+    xy, yz, c, N, na, nb = load_table(mol)
+    if not sector:
+        na = nb = None
+    return nb200.DeviceTermTable(xy, yz, c, N, na, nb), c_oracle.COracleTable(xy, yz, c, N, na, nb), (N, na, nb)
+
+
+# ------------------------------------------------------------------------------------------- golden
+@pytest.mark.parametrize("name", sorted(CASE_TABLE))
+def test_eloc_matches_reference_fixture(name):
+    nb200, _, _ = _mods()
+    case = load_case(name)
+    xy, yz, c, N, _, _ = load_table(CASE_TABLE[name])
+    na, nb = case_sector(case, name)
+    t = nb200.DeviceTermTable(xy, yz, c, N, na, nb)
+    before = nb200.launch_count()
+    e = gpu_eloc(t, case["states"], case["psi"])
+    assert nb200.launch_count() > before, "no kernel of libnaqs_eloc.so was launched"
+    assert rel_err(e, case["eloc"]).max() <= ELOC_RTOL
+    # hash lookup gives the same numbers as the dense (direct-address) lookup, bit for bit
+    e_hash = gpu_eloc(t, case["states"], case["psi"], kind=nb200._lib.LOOKUP_HASH)
+    e_dense = gpu_eloc(t, case["states"], case["psi"], kind=nb200._lib.LOOKUP_DENSE)
+    assert np.array_equal(e_hash, e_dense) and np.array_equal(e_dense, e)
+    # complex128 psi carrying the same values gives identical results (exact promotion, sparse_math.pyx:33-37)
+    assert np.array_equal(gpu_eloc(t, case["states"], case["psi"].astype(np.complex128)), e)
+    # host-buffer entry (naqs_eloc_host) == device-buffer entry
+    assert np.array_equal(t.local_energy_host(case["states"], case["psi"]), e)
+
+
+@pytest.mark.parametrize("name", ["LiH_sector", "LiH_small", "H2O_sector", "LiH_full_600"])
+def test_rows_match_reference_csr_bit_exact(name):
+    nb200, _, _ = _mods()
+    case = load_case(name)
+    xy, yz, c, N, _, _ = load_table(CASE_TABLE[name])
+    na, nb = case_sector(case, name)
+    t = nb200.DeviceTermTable(xy, yz, c, N, na, nb)
+    indptr, cols, ridx, vals = (x.cpu().numpy() for x in t.rows(case["states"]))
+    assert np.array_equal(indptr, case["rows_indptr"])
+    for m in range(len(indptr) - 1):
+        lo, hi = indptr[m], indptr[m + 1]
+        o = np.argsort(ridx[lo:hi], kind="stable")
+        assert np.array_equal(ridx[lo:hi][o], case["rows_cols_restricted"][lo:hi])
+        assert np.array_equal(cols[lo:hi, 0][o].view(np.uint64), case["rows_cols_keys"][lo:hi])
+        assert np.array_equal(vals[lo:hi][o], case["rows_vals"][lo:hi])
+    # coupled-state set (radix sort + unique on the device) == np.unique of the reference's columns
+    uniq = t.coupled_state_set(case["states"])[:, 0].cpu().numpy().view(np.uint64)
+    assert np.array_equal(uniq, np.unique(case["rows_cols_keys"]))
+    assert np.array_equal(np.sort(t.restricted_index(uniq.view(np.int64)).cpu().numpy()), case["coupled_unique_restricted"])
+
+
+# ------------------------------------------------------------------------------------------- oracle, seeded
+@pytest.mark.parametrize("mol,m,sector", [("LiH", 225, True), ("H2O", 441, True), ("NH3", 3136, True), ("N2", 14400, True),
+                                          ("N2_2.25", 5000, True), ("C2", 8000, True), ("H2S", 3000, True), ("Li2O", 3000, True),
+                                          ("N2", 20000, False), ("H2O", 16384, False), ("Li2O", 1500, False)])
+def test_eloc_vs_oracle(mol, m, sector):
+    nb200, c_oracle, eo = _mods()
+    t, ct, (N, na, nb) = make_tables(mol, sector)
+    if sector:
+        sec_size = eo.comb((N + 1) // 2, na) * eo.comb(N // 2, nb)
+        st = eo.sector_keys(N, na, nb)[:, 0] if sec_size <= m else random_sector_states(N, na, nb, m, seed=7)
+        st = st[np.random.default_rng(3).permutation(len(st))]
+    else:
+        st = random_keys(N, m, seed=5)
+    psi = eo.synthetic_psi(len(st), seed=11)
+    e = gpu_eloc(t, st, psi)
+    ref = ct.local_energy(st, psi)
+    assert rel_err(e, ref).max() <= ELOC_RTOL
+    assert np.all(np.isfinite(e.view(np.float64)))
+
+
+@pytest.mark.parametrize("mol,m,sector", [("LiH", 225, True), ("N2", 3000, True), ("N2", 3000, False), ("Li2O", 500, True), ("H2S", 700, True)])
+def test_rows_and_hij_vs_oracle_bit_exact(mol, m, sector):
+    nb200, c_oracle, eo = _mods()
+    t, ct, (N, na, nb) = make_tables(mol, sector)
+    if sector:
+        st = random_sector_states(N, na, nb, min(m, eo.comb((N + 1) // 2, na) * eo.comb(N // 2, nb)), seed=21)
+    else:
+        st = random_keys(N, m, seed=22)
+    indptr, cols, ridx, vals = (x.cpu().numpy() for x in t.rows(st))
+    i2, c2, v2 = ct.rows(st)
+    assert np.array_equal(indptr, i2)
+    assert np.array_equal(cols.view(np.uint64), c2)          # coupled-state sets, in the same (XY) order
+    assert np.array_equal(vals, v2)                          # matrix elements incl. signs, bit-exact
+    assert np.array_equal(ridx, ct.restricted_index(c2))
+    h = t.hij_dense(st[:200]).cpu().numpy()
+    assert np.array_equal(h.reshape(-1), ct.hij_dense(st[:200]))
+    uniq = t.coupled_state_set(st)[:, 0].cpu().numpy().view(np.uint64)
+    assert np.array_equal(uniq, np.unique(c2[:, 0]))
+
+
+@pytest.mark.parametrize("N,K,M", [(40, 1500, 3000), (63, 4000, 2000), (100, 3000, 2500), (127, 1000, 1000), (20, 30000, 500)])
+def test_wide_and_large_synthetic_tables(N, K, M):
+    """64-/128-bit masks and tables larger than one shared-memory tile."""
+    nb200, c_oracle, eo = _mods()
+    xy, yz, c = eo.synthetic_table(N, K, seed=N + K)
+    st = eo.synthetic_states(N, M, seed=N)
+    psi = eo.synthetic_psi(M, seed=K)
+    t, ct = nb200.DeviceTermTable(xy, yz, c, N), c_oracle.COracleTable(xy, yz, c, N)
+    # the lookup table = the batch plus every coupled state of its first 50 members, so that many lookups hit
+    _, cols, _ = ct.rows(st[:50])
+    tk = np.unique(np.concatenate([st, cols]), axis=0)
+    tp = eo.synthetic_psi(len(tk), seed=5)
+    e = gpu_eloc(t, st, psi, table_keys=tk, table_psi=tp)
+    ref = ct.local_energy(st, psi, tk, tp)
+    assert rel_err(e, ref).max() <= ELOC_RTOL
+    indptr, cols_g, _, vals = (x.cpu().numpy() for x in t.rows(st[:300], with_restricted_index=False))
+    i2, c2, v2 = ct.rows(st[:300])
+    assert np.array_equal(indptr, i2) and np.array_equal(cols_g.view(np.uint64), c2) and np.array_equal(vals, v2)
+    uniq = t.unique_keys(c2).cpu().numpy().view(np.uint64)
+    exp = np.unique(c2, axis=0)
+    exp = exp[np.lexsort(tuple(exp[:, w] for w in range(exp.shape[1])))]
+    assert np.array_equal(uniq, exp)
+
+
+# ------------------------------------------------------------------------------------------- edge cases
+def test_edge_cases():
+    nb200, c_oracle, eo = _mods()
+    t, ct, (N, na, nb) = make_tables("LiH", True)
+    sec = eo.sector_keys(N, na, nb)[:, 0]
+    psi = eo.synthetic_psi(len(sec), 1)
+    # empty batch
+    assert gpu_eloc(t, sec[:0], psi[:0]).shape == (0,)
+    ip, cols, ridx, vals = t.rows(sec[:0])
+    assert ip.cpu().numpy().tolist() == [0] and cols.shape[0] == 0
+    # single state: only the diagonal couples
+    e1 = gpu_eloc(t, sec[:1], psi[:1])
+    assert rel_err(e1, ct.local_energy(sec[:1], psi[:1])).max() <= ELOC_RTOL and abs(e1[0].imag) == 0
+    # ragged sizes around the CTA tile (256 threads x 4 states)
+    for m in (31, 33, 255, 1023, 1024, 1025):
+        st = np.resize(sec, m)  # rows may repeat (the "with replacement" throughput config of SURVEY.md §8d)
+        p = eo.synthetic_psi(m, m)
+        tk, tp = sec, psi
+        assert rel_err(gpu_eloc(t, st, p, table_keys=tk, table_psi=tp), ct.local_energy(st, p, tk, tp)).max() <= ELOC_RTOL
+    # duplicate table keys are summed like scipy's repeated column (SURVEY.md §8 input contract)
+    tk = np.concatenate([sec[:100], sec[:10]])
+    tp = eo.synthetic_psi(110, 9)
+    e = gpu_eloc(t, sec[:100], tp[:100], table_keys=tk, table_psi=tp)
+    assert rel_err(e, ct.local_energy(sec[:100], tp[:100], tk, tp)).max() <= 1e-11
+    # a state outside the sector has no stored couplings (its couplings all fail the sector mask)
+    bad = np.array([0b111], dtype=np.uint64)
+    ip, _, _, _ = t.rows(bad)
+    assert ip.cpu().numpy().tolist() == ct.rows(bad)[0].tolist()
+    # empty term table
+    t0 = nb200.DeviceTermTable(np.zeros(0, np.uint64), np.zeros(0, np.uint64), np.zeros(0), N, na, nb)
+    assert np.all(gpu_eloc(t0, sec[:10], psi[:10]) == 0)
+    # E_loc before any lookup table exists is a call-order error, not garbage
+    t2, _, _ = make_tables("LiH", True)
+    buf = torch.zeros(64, dtype=torch.int64, device="cuda")
+    with pytest.raises(nb200.NaqsError):
+        nb200._lib.check(nb200._lib.load().naqs_eloc(t2._h, nb200._lib.ptr(buf), nb200._lib.ptr(buf), 0, 4, nb200._lib.ptr(buf), None))
+
+
+def test_device_resident_inputs_and_streams():
+    nb200, c_oracle, eo = _mods()
+    t, ct, (N, na, nb) = make_tables("N2", True)
+    st = random_sector_states(N, na, nb, 4096, seed=2)
+    psi = eo.synthetic_psi(4096, 3)
+    d_st = torch.from_numpy(st.view(np.int64)).cuda()
+    d_psi = torch.from_numpy(psi).cuda()
+    ref = ct.local_energy(st, psi)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        out = t.local_energy(d_st, d_psi)
+    s.synchronize()
+    assert rel_err(nb200._lib.complex_from_pairs(out), ref).max() <= ELOC_RTOL
+    # [M, 2] float32 torch layout, as the reference's optimizer hands psi over (complex.py)
+    out2 = t.local_energy(d_st, torch.view_as_real(d_psi))
+    assert torch.equal(out, out2)
+
+
+# ------------------------------------------------------------------------------------------- level-0 twins
+def test_level0_twins_match_reference_outputs():
+    nb200, _, _ = _mods()
+    from scipy.sparse import csr_matrix
+    hm, sm, him = nb200.hamiltonian_math, nb200.sparse_math, nb200.hilbert_math
+    d = np.load(os.path.join(GOLDEN, "level0.npz"))
+    for dt in ("int8", "uint8", "int16", "uint16", "int32", "uint32", "int64", "uint64"):
+        out = hm.popcount_parity(d[f"pp_in_{dt}"])
+        assert out.dtype == np.int8 and np.array_equal(out, d[f"pp_out_{dt}"])
+    out = hm.popcount_parity(d["pp_in_1d"])
+    assert out.shape == (19, 1) and np.array_equal(out, d["pp_out_1d"])
+    with pytest.raises(TypeError):
+        hm.popcount_parity(np.zeros(4, np.float32))
+    for cd in (np.float64, np.float32):
+        H = hm.get_Hij_cy(d["hij_states"], d["hij_uXY"], d["hij_u2aXY"], d["hij_P"], d["hij_u2aYZ"], d["hij_c"].astype(cd))
+        assert H.dtype == cd and np.array_equal(H, d[f"hij_out_{np.dtype(cd).name}"])
+    n = len(d["mv_indptr"]) - 1
+    H = csr_matrix((d["mv_data"], d["mv_indices"], d["mv_indptr"]), shape=(n, n))
+    assert np.array_equal(sm.sparse_dense_mv(H, d["mv_v128"]), d["mv_out128"])
+    assert np.array_equal(sm.sparse_dense_mv(H, d["mv_v64"]), d["mv_out64"])          # c64 promoted to c128
+    assert np.array_equal(sm.sparse_dense_mv(H, d["mv_vreal"]), d["mv_outreal"])      # real promoted to c128
+    assert np.array_equal(sm.sparse_dense_mv(H, d["mv_v128"], par=False), d["mv_out_serial"])
+    H32 = H.astype(np.float32)
+    o = sm.sparse_dense_mv(H32, d["mv_v64"])
+    assert o.dtype == np.complex64 and np.array_equal(o, d["mv32_out64"])
+    assert np.array_equal(sm.sparse_dense_mv(H32, d["mv_v128"]), d["mv32_out128"])
+    assert np.array_equal(sm.sparse_sparse_mv(H, d["ssmv_v"], d["ssmv_idx"]), d["ssmv_out"])
+    assert np.array_equal(him.make_basis_idxs_cy(4), d["basis4"]) and np.array_equal(him.make_basis_idxs_cy(9), d["basis9"])
+
+
+def test_level0_pipeline_equals_fused_rows():
+    """The Level-0 chain AND -> popcount_parity -> get_Hij_cy (hamiltonian.py:301-337) on the device equals hij_dense."""
+    nb200, c_oracle, eo = _mods()
+    xy, yz, c, N, na, nb = load_table("H2O")
+    t = nb200.DeviceTermTable(xy, yz, c, N, na, nb)
+    st = random_sector_states(N, na, nb, 100, seed=4).astype(np.int64).astype(np.int16)
+    uXY, u2aXY = np.unique(xy.astype(np.int64).astype(np.int16), return_inverse=True)
+    uYZ, u2aYZ = np.unique(yz.astype(np.int64).astype(np.int16), return_inverse=True)
+    P = nb200.hamiltonian_math.popcount_parity(np.bitwise_and(st[:, None], uYZ[None, :]))
+    H = nb200.hamiltonian_math.get_Hij_cy(st, uXY, u2aXY, P, u2aYZ, c)
+    assert np.array_equal(H, t.hij_dense(st).cpu().numpy().reshape(-1))
+
+
+def test_state2idx_restricted_index_and_stats():
+    nb200, c_oracle, eo = _mods()
+    lib, L = nb200._lib.load(), nb200._lib
+    rng = np.random.default_rng(0)
+    for N in (12, 30, 40, 100):
+        W = L.n_words(N)
+        s = (rng.integers(0, 2, size=(777, N)).astype(np.int8) * 2 - 1)
+        d_s = torch.from_numpy(s).cuda()
+        d_k = torch.empty((777, W), dtype=torch.int64, device="cuda")
+        L.check(lib.naqs_state2idx(L.ptr(d_s), 777, N, W, L.ptr(d_k), None))
+        assert np.array_equal(d_k.cpu().numpy().view(np.uint64), eo.state2idx(s))
+    t, ct, (N, na, nb) = make_tables("H2O", True)
+    allk = np.arange(2 ** N, dtype=np.uint64)
+    assert np.array_equal(t.restricted_index(allk).cpu().numpy(), ct.restricted_index(allk))
+    t30, ct30, (N, na, nb) = make_tables("Li2O", True)
+    ks = random_sector_states(N, na, nb, 5000, seed=1)
+    assert np.array_equal(t30.restricted_index(ks).cpu().numpy(), ct30.restricted_index(ks))
+    e = (rng.normal(size=100001) + 1j * rng.normal(size=100001))
+    w = rng.random(100001)
+    s5 = t.stats(e, w).cpu().numpy()
+    exp = np.array([w.sum(), (w * e.real).sum(), (w * e.imag).sum(), (w * e.real ** 2).sum(), len(e)])
+    assert np.allclose(s5, exp, rtol=1e-12, atol=0)
+    assert np.allclose(t.stats(e).cpu().numpy()[[0, 4]], [len(e), len(e)])
+
+
+# ------------------------------------------------------------------------------------------- mirror classes
+def test_pauli_hamiltonian_mirror_known_answers():
+    nb200, _, eo = _mods()
+    with open(os.path.join(GOLDEN, "known_answers.json")) as f:
+        known = json.load(f)
+    for mol in ("LiH", "H2O", "NH3"):
+        xy, yz, c, N, na, nb = load_table(mol)
+        # rebuild a terms dict from the packed table is impossible; drive the mirror through its table directly
+        hil = nb200.Hilbert.get(N, na, nb, encoding=nb200.Encoding.SIGNED)
+        ph = nb200.PauliHamiltonianB200.__new__(nb200.PauliHamiltonianB200)
+        _init_mirror_from_table(ph, hil, xy, yz, c)
+        sec = hil.get_subspace(ret_states=False, ret_idxs=True)
+        H = ph.update_H(sec, check_unseen=False, assume_unique=True)
+        assert H.nnz == known[mol]["nnz"] and H.shape == (known[mol]["sector"],) * 2
+        assert abs(H.diagonal().sum() - known[mol]["trace"]) <= 1e-12 * abs(known[mol]["trace"])
+        assert abs(np.abs(H.data).sum() - known[mol]["sum_abs"]) <= 1e-12 * known[mol]["sum_abs"]
+        assert abs(H - H.T).max() == 0
+        if mol != "NH3":
+            assert abs(np.linalg.eigvalsh(H.toarray())[0] - known[mol]["e0"]) < 1e-9
+        # cache semantics: a second update with check_unseen=True adds nothing (hamiltonian.py:294-299)
+        assert ph.update_H(sec, check_unseen=True, assume_unique=True).nnz == H.nnz
+        sub = sec[:50]
+        Hs = ph.get_H(sub)
+        assert Hs.shape == (50, 50)
+        ph.freeze_H()
+        assert ph.is_frozen() and ph.get_restricted_H().nnz == H.nnz
+
+
+def _init_mirror_from_table(ph, hil, xy, yz, c, device=None):
+    """Build a PauliHamiltonianB200 from an already packed table (fixtures hold tables, not Pauli strings)."""
+    import naqs_b200
+    from scipy.sparse import csr_matrix
+    ph.hilbert, ph.dtype, ph.verbose, ph.n_excitations_max, ph.qubit_hamiltonian = hil, np.float64, False, None, None
+    ph.restricted_idxs = hil.full2restricted_idx(hil.get_subspace(ret_states=False, ret_idxs=True))
+    ph.table = naqs_b200.DeviceTermTable(xy, yz, c, hil.N, hil.N_alpha, hil.N_beta, device)
+    ph.H = csr_matrix(([], ([], [])), shape=(hil.size, hil.size), dtype=np.float64)
+    ph._cached_idxs = np.array([], dtype=hil.get_idx_dtype("np"))
+    ph._frozen_H, ph._restricted_H = False, None
+
+
+def test_pauli_hamiltonian_from_pauli_strings_and_calculate_local_energy():
+    """End to end through the reference-shaped API: Pauli strings -> PauliHamiltonian.get -> calculate_local_energy."""
+    import types
+    from conftest import load_terms_json
+    nb200, c_oracle, eo = _mods()
+    case = load_case("LiH_sector")
+    N, na, nb = 12, 2, 2
+    hil = nb200.Hilbert.get(N, na, nb, encoding=nb200.Encoding.SIGNED)
+    op = types.SimpleNamespace(terms=load_terms_json("LiH"))
+    sec = hil.get_subspace(ret_states=False, ret_idxs=True)
+    ph = nb200.PauliHamiltonian.get(hil, op, restricted_idxs=sec, dtype=np.float64)
+    assert (ph.table.K, ph.table.Kxy, ph.table.Kyz) == (631, 84, 252)
+    opt = types.SimpleNamespace(pauli_hamiltonian=ph, hilbert=hil)
+    idx = torch.from_numpy(case["states"].astype(np.int64).astype(np.int16)).unsqueeze(-1)
+    psi_t = torch.view_as_real(torch.from_numpy(case["psi"]))  # float32 [M, 2], as energy.py:310 passes it
+    e32 = nb200.calculate_local_energy(opt, idx.squeeze(), psi=psi_t)
+    assert e32.dtype == torch.float32 and e32.shape == (len(idx), 2)
+    ec = nb200.calculate_local_energy(opt, idx.squeeze(), psi=psi_t, ret_complex=True)
+    assert rel_err(ec, case["eloc"]).max() <= ELOC_RTOL
+    assert torch.equal(e32, torch.FloatTensor(np.stack([case["eloc"].real, case["eloc"].imag], -1)))
+    with pytest.raises(NotImplementedError):
+        nb200.calculate_local_energy(opt, idx.squeeze(), psi=psi_t, set_unsampled_states_to_zero=False)
+    # update_H rows through the mirror == the reference CSR rows of the fixture
+    H = ph.update_H(idx, check_unseen=True, assume_unique=True)
+    r = np.asarray(hil.full2restricted_idx(idx.squeeze().numpy())).astype(np.int64)
+    got_cols = np.concatenate([H.indices[H.indptr[i]:H.indptr[i + 1]] for i in r])
+    got_vals = np.concatenate([H.data[H.indptr[i]:H.indptr[i + 1]] for i in r])
+    assert np.array_equal(got_cols, case["rows_cols_restricted"]) and np.array_equal(got_vals, case["rows_vals"])
+    assert np.array_equal(np.asarray(ph.get_coupled_state_idxs(r, return_unique=True)), case["coupled_unique_restricted"])
+
+
+# ------------------------------------------------------------------------------------------- full-size properties
+def test_full_size_properties_n2_1e6():
+    """BASELINE config 3 at full size (N2, M = 1e6 distinct keys of the 2^20 space): size-independent properties
+    + an oracle check on a sub-sample."""
+    nb200, c_oracle, eo = _mods()
+    xy, yz, c, N, _, _ = load_table("N2")
+    t, ct = nb200.DeviceTermTable(xy, yz, c, N), c_oracle.COracleTable(xy, yz, c, N)
+    rng = np.random.default_rng(0)
+    st = rng.choice(2 ** N, 1_000_000, replace=False).astype(np.uint64)
+    psi = eo.synthetic_psi(len(st), 0)
+    e = gpu_eloc(t, st, psi)
+    assert np.all(np.isfinite(e.view(np.float64)))
+    # (1) scale invariance: E_loc(a psi) = E_loc(psi) for a power-of-two scale (exact in floating point)
+    assert np.array_equal(gpu_eloc(t, st, psi * np.complex64(4.0)), e)
+    # (2) permutation equivariance
+    perm = rng.permutation(len(st))
+    assert np.array_equal(gpu_eloc(t, st[perm], psi[perm]), e[perm])
+    # (3) Hermiticity: sum_s |psi_s|^2 E_loc(s)^* = <psi|H|psi> restricted to the batch is real
+    p = psi.astype(np.complex128)
+    tot = np.sum(np.abs(p) ** 2 * np.conj(e))
+    assert abs(tot.imag) <= 1e-9 * abs(tot.real)
+    # (4) oracle on a sub-sample of rows against the full table
+    sub = rng.choice(len(st), 3000, replace=False)
+    ref = ct.local_energy(st[sub], psi[sub], st, psi)
+    assert rel_err(e[sub], ref).max() <= ELOC_RTOL
+    # (5) hash lookup == dense lookup at full size
+    assert np.array_equal(gpu_eloc(t, st, psi, kind=nb200._lib.LOOKUP_HASH), e)
+
+
+def test_full_size_li2o_1e5():
+    """BASELINE config 4 batch (Li2O, 30 qubits, K = 20 558 > one smem tile, M = 1e5 sector states)."""
+    nb200, c_oracle, eo = _mods()
+    t, ct, (N, na, nb) = make_tables("Li2O", True)
+    st = random_sector_states(N, na, nb, 100_000, seed=0)
+    psi = eo.synthetic_psi(len(st), 1)
+    e = gpu_eloc(t, st, psi)
+    sub = np.random.default_rng(1).choice(len(st), 1500, replace=False)
+    ref = ct.local_energy(st[sub], psi[sub], st, psi)
+    assert rel_err(e[sub], ref).max() <= ELOC_RTOL
+    assert np.array_equal(gpu_eloc(t, st, psi * np.complex64(0.5)), e)
