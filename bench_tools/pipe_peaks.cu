@@ -17,7 +17,7 @@ __global__ void k_popc(uint32_t* out, uint32_t seed) {
     for (int i = 0; i < ILP; ++i) x[i] = threadIdx.x * 2654435761u + i + seed;
     for (int it = 0; it < ITERS; ++it)
 #pragma unroll
-        for (int i = 0; i < ILP; ++i) x[i] = __popc(x[i]) + 0x55555555u;   // POPC + IADD (alu); POPC is the slow one
+        for (int i = 0; i < ILP; ++i) asm volatile("popc.b32 %0, %0;" : "+r"(x[i]));
     uint32_t s = 0;
     for (int i = 0; i < ILP; ++i) s ^= x[i];
     if (s == 0xdeadbeef) out[0] = s;
@@ -28,7 +28,7 @@ __global__ void k_lop3(uint32_t* out, uint32_t seed) {
     const uint32_t a = seed * 3 + 1, b = seed * 7 + 5;
     for (int it = 0; it < ITERS; ++it)
 #pragma unroll
-        for (int i = 0; i < ILP; ++i) x[i] = (x[i] & a) ^ (b + i);
+        for (int i = 0; i < ILP; ++i) asm volatile("lop3.b32 %0, %0, %1, %2, 0x6a;" : "+r"(x[i]) : "r"(a), "r"(b));
     uint32_t s = 0;
     for (int i = 0; i < ILP; ++i) s ^= x[i];
     if (s == 0xdeadbeef) out[0] = s;

@@ -148,7 +148,9 @@ def test_wide_and_large_synthetic_tables(N, K, M):
     e = gpu_eloc(t, st, psi, table_keys=tk, table_psi=tp)
     ref = ct.local_energy(st, psi, tk, tp)
     assert rel_err(e, ref).max() <= ELOC_RTOL
-    indptr, cols_g, _, vals = (x.cpu().numpy() for x in t.rows(st[:300], with_restricted_index=False))
+    indptr, cols_g, ridx_none, vals = t.rows(st[:300], with_restricted_index=False)
+    assert ridx_none is None
+    indptr, cols_g, vals = indptr.cpu().numpy(), cols_g.cpu().numpy(), vals.cpu().numpy()
     i2, c2, v2 = ct.rows(st[:300])
     assert np.array_equal(indptr, i2) and np.array_equal(cols_g.view(np.uint64), c2) and np.array_equal(vals, v2)
     uniq = t.unique_keys(c2).cpu().numpy().view(np.uint64)
