@@ -93,6 +93,11 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
 int naqs_eloc(naqs_table_t* t, const uint64_t* d_states, const void* d_psi, int psi_dtype, int64_t n_states,
               double* d_eloc, void* stream);
 
+/* Kernel formulation used by naqs_eloc: 0 = nibble-sliced parity + group LUT (default), 1 = direct
+ * AND/POPC walk (the formulation of hamiltonian_math.pyx:449-451, 31-34 transcribed; kept for A/B checks).
+ * Both give bit-identical H_ij.  The environment variable NAQS_ELOC_ALGO=direct sets the default. */
+int naqs_table_set_algo(naqs_table_t* t, int algo);
+
 /* Same through HOST buffers (what a caller holding numpy arrays uses; bench.py's e2e leg): uploads
  * states + psi, builds the lookup table from the same (states, psi) batch, runs naqs_eloc and
  * downloads E_loc.  Synchronous.  h_table_keys may be NULL (=> the batch is its own table, the

@@ -28,6 +28,7 @@ SIGNATURES = {
     "naqs_table_info": (_i, [_p, _p]),
     "naqs_lookup_build": (_i, [_p, _p, _p, _i, _i64, _i, _p]),
     "naqs_eloc": (_i, [_p, _p, _p, _i, _i64, _p, _p]),
+    "naqs_table_set_algo": (_i, [_p, _i]),
     "naqs_eloc_host": (_i, [_p, _p, _p, _i, _i64, _p, _p, _i64, _p]),
     "naqs_rows_count": (_i, [_p, _p, _i64, _p, _p]),
     "naqs_exclusive_scan": (_i, [_p, _p, _i64, _p, _p]),

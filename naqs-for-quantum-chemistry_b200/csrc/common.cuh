@@ -117,6 +117,15 @@ struct naqs_table {
     naqs::Tile* d_tiles = nullptr;
     int n_tiles = 0, tile_cap = 0;
     long long* d_binom = nullptr;  // C(n, k) table for the restricted-index ranker (lazy)
+    // sliced (v2) formulation: byte stream + tile lists for the 1024/512/256-thread launch shapes
+    int algo = 0;                  // 0 = sliced (default), 1 = direct
+    unsigned char* d_stream = nullptr;
+    size_t stream_bytes = 0;
+    void* d_stiles[3] = {nullptr, nullptr, nullptr};
+    int n_stiles[3] = {0, 0, 0};
+    int nn = 0;
+    double2* d_partial = nullptr;
+    size_t partial_bytes = 0;
     // lookup
     int lookup_kind = 0;  // 0 = none
     int64_t lookup_n = 0;

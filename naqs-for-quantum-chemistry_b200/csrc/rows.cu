@@ -80,7 +80,7 @@ int naqs_rows_count(naqs_table_t* t, const uint64_t* d_states, int64_t M, int64_
 int naqs_rows_fill(naqs_table_t* t, const uint64_t* d_states, int64_t M, const int64_t* d_indptr, uint64_t* d_col_keys,
                    int64_t* d_col_ridx, double* d_vals, void* stream) {
     NAQS_REQUIRE(t, NAQS_ERR_ARG, "naqs_rows_fill: NULL table");
-    NAQS_REQUIRE(M >= 0 && (M == 0 || (d_states && d_indptr && d_col_keys && d_vals)), NAQS_ERR_ARG, "naqs_rows_fill: NULL buffers");
+    NAQS_REQUIRE(M >= 0 && (M == 0 || (d_states && d_indptr)), NAQS_ERR_ARG, "naqs_rows_fill: NULL buffers");  // col/val buffers may be NULL when nnz == 0
     if (M == 0) return NAQS_OK;
     DeviceGuard guard(t->device);
     if (d_col_ridx) { int rc = ensure_binom(t); if (rc) return rc; }

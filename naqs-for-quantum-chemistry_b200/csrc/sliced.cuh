@@ -1,0 +1,429 @@
+// sliced.cuh — the "nibble-sliced parity + group LUT" formulation of the fused E_loc kernel (v2).
+//
+// Why: in the direct formulation every (state, term) pair costs AND + POPC + shift + XOR + DADD, and POPC
+// issues at 16 lanes/clk/SM on sm_100a (measured: 4.0e12 couplings/s ceiling, profiles/pipe_peaks_*.json).
+// Here the 32 parities of a WORD of terms are produced at once for one state,
+//     P_w(s) = XOR_i  T[w][i][ nibble_i(s) ]            (one 4-byte LDS per 4 qubits, no POPC),
+// where T[w][i][v] holds, for each of the 32 terms of word w, the parity of popcount(yz_term & (v << 4i)).
+// XY groups of <= 4 (<= 6) terms occupy 4 (6) adjacent bits of a word, and the group's matrix element
+//     H[s, s^u] = sum_k c_k (-1)^{p_k}     (k ascending, src_cpp/hamiltonian_math.pyx:31-34)
+// is read from a 16- (64-) entry table indexed by those parity bits.  Every table entry was produced by
+// the same serial fp64 additions, in the same order, as the reference performs — so H is bit-identical —
+// but the device does one LDS.64 instead of n x (POPC, XOR, DADD).  Larger groups (the diagonal, the
+// 2-flip groups) keep the serial walk, their signs taken from the parity word (shift + XOR + DADD).
+//
+// Stream layout (device memory, staged into shared memory tile by tile with cp.async.bulk + mbarrier):
+//   A record (8 groups x 4 bits):  T[NN][16] u32 | U[8][NW] u32 | LUT[8][16] f64
+//   B record (5 groups x 6 bits):  T[NN][16] u32 | U[8][NW] u32 | LUT[5][64] f64
+//   C blob   (one big group)    :  header{n_words, n_sub8, flags, -, u[4]} | n_words x ( T[NN][16] u32 | c[32] f64 )
+#pragma once
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "eloc_kernels.cuh"
+
+namespace naqs {
+
+enum { kSecA = 0, kSecB = 1, kSecC = 2 };
+constexpr uint32_t kBlobFirst = 1u, kBlobLast = 2u;
+
+struct STile {
+    uint32_t kind;      // kSecA / kSecB / kSecC
+    uint32_t count;     // records (A, B) or blobs (C)
+    uint32_t bytes;     // multiple of 16
+    uint32_t pad;
+    uint64_t offset;    // byte offset into the stream, multiple of 16
+};
+
+struct SlicedView {
+    const unsigned char* stream;
+    const STile* tiles;
+    int n_tiles;
+    int nn;             // nibbles per key (5, 8, 16 or 32)
+};
+
+// ------------------------------------------------------------------------------------------ host builder
+struct HostGroup {
+    uint32_t u[4];
+    std::vector<uint32_t> yz;  // [n][NW]
+    std::vector<double> c;
+};
+
+inline int nibbles_for(int n_qubits) { return n_qubits <= 20 ? 5 : (n_qubits <= 32 ? 8 : (n_qubits <= 64 ? 16 : 32)); }
+inline size_t rec_bytes_A(int nn, int nw) { return (size_t)64 * nn + 32 * nw + 8 * 16 * 8; }
+inline size_t rec_bytes_B(int nn, int nw) { return (size_t)64 * nn + 32 * nw + 5 * 64 * 8; }
+inline size_t rec_bytes_C(int nn) { return (size_t)64 * nn + 256; }
+constexpr size_t kBlobHeader = 32;
+
+struct SlicedHost {
+    std::vector<unsigned char> stream;
+    int nn = 0, nw = 0;
+    size_t n_rec_a = 0, n_rec_b = 0;
+    struct Blob { size_t offset, bytes; };
+    std::vector<Blob> blobs;
+    size_t off_a = 0, off_b = 0, off_c = 0;
+};
+
+// parity nibble tables of up to 32 terms (yz pointers may be null = padding term, parity 0)
+inline void fill_nibble_tables(unsigned char* dst, int nn, int nw, const uint32_t* const* yz_of_bit, int n_bits) {
+    uint32_t* T = reinterpret_cast<uint32_t*>(dst);
+    for (int i = 0; i < nn; ++i)
+        for (int v = 0; v < 16; ++v) {
+            uint32_t word = 0;
+            for (int b = 0; b < n_bits; ++b) {
+                const uint32_t* yz = yz_of_bit[b];
+                if (!yz) continue;
+                const int w = (4 * i) / 32, sh = (4 * i) % 32;
+                if (w >= nw) continue;
+                const uint32_t nib = (yz[w] >> sh) & 15u;
+                word |= (uint32_t)(__builtin_popcount(nib & (uint32_t)v) & 1) << b;
+            }
+            T[i * 16 + v] = word;
+        }
+}
+
+// serial signed sum in reference order: pattern bit t set => term t enters with a minus sign
+inline double lut_entry(const double* c, int n, unsigned pattern) {
+    volatile double acc = 0.0;  // volatile: every addition individually rounded, no re-association
+    for (int t = 0; t < n; ++t) acc = acc + (((pattern >> t) & 1u) ? -c[t] : c[t]);
+    return acc;
+}
+
+inline void build_sliced_host(const std::vector<HostGroup>& groups, int n_qubits, int nw, size_t max_blob_bytes, SlicedHost& out) {
+    const int nn = nibbles_for(n_qubits);
+    out.nn = nn; out.nw = nw;
+    std::vector<const HostGroup*> ga, gb, gc;
+    for (const auto& g : groups) {
+        const size_t n = g.c.size();
+        (n <= 4 ? ga : (n <= 6 ? gb : gc)).push_back(&g);
+    }
+    const size_t ra = rec_bytes_A(nn, nw), rb = rec_bytes_B(nn, nw), rc = rec_bytes_C(nn);
+    out.n_rec_a = (ga.size() + 7) / 8;
+    out.n_rec_b = (gb.size() + 4) / 5;
+    auto& S = out.stream;
+    S.clear();
+    out.off_a = 0;
+    S.resize(out.n_rec_a * ra, 0);
+    auto pack = [&](const std::vector<const HostGroup*>& gs, size_t n_rec, size_t rec, int per, int bits, size_t base) {
+        for (size_t r = 0; r < n_rec; ++r) {
+            unsigned char* p = S.data() + base + r * rec;
+            const uint32_t* yz_of_bit[32] = {nullptr};
+            uint32_t* U = reinterpret_cast<uint32_t*>(p + 64 * nn);
+            double* L = reinterpret_cast<double*>(p + 64 * nn + 32 * nw);
+            for (int j = 0; j < per; ++j) {
+                const size_t gi = r * per + j;
+                const HostGroup* g = gi < gs.size() ? gs[gi] : nullptr;
+                const int n = g ? (int)g->c.size() : 0;
+                for (int t = 0; t < n; ++t) yz_of_bit[j * bits + t] = g->yz.data() + (size_t)t * nw;
+                for (int w = 0; w < nw; ++w) U[j * nw + w] = g ? g->u[w] : 0u;
+                for (unsigned pat = 0; pat < (1u << bits); ++pat) L[j * (1 << bits) + pat] = g ? lut_entry(g->c.data(), n, pat) : 0.0;
+            }
+            fill_nibble_tables(p, nn, nw, yz_of_bit, per * bits);
+        }
+    };
+    pack(ga, out.n_rec_a, ra, 8, 4, out.off_a);
+    out.off_b = S.size();
+    S.resize(S.size() + out.n_rec_b * rb, 0);
+    pack(gb, out.n_rec_b, rb, 5, 6, out.off_b);
+    out.off_c = S.size();
+    // big groups: blobs of at most max_words words
+    const size_t max_words = std::max<size_t>(1, (max_blob_bytes - kBlobHeader) / rc);
+    for (const HostGroup* g : gc) {
+        const size_t n = g->c.size(), total_words = (n + 31) / 32;
+        for (size_t w0 = 0; w0 < total_words; w0 += max_words) {
+            const size_t nwords = std::min(max_words, total_words - w0);
+            const size_t t0 = w0 * 32, t1 = std::min(n, (w0 + nwords) * 32);
+            const size_t off = S.size();
+            S.resize(off + kBlobHeader + nwords * rc, 0);
+            uint32_t* hdr = reinterpret_cast<uint32_t*>(S.data() + off);
+            hdr[0] = (uint32_t)nwords;
+            hdr[1] = (uint32_t)((t1 - t0 + 7) / 8);
+            hdr[2] = (w0 == 0 ? kBlobFirst : 0u) | (w0 + nwords >= total_words ? kBlobLast : 0u);
+            for (int w = 0; w < nw; ++w) hdr[4 + w] = g->u[w];
+            for (size_t q = 0; q < nwords; ++q) {
+                unsigned char* p = S.data() + off + kBlobHeader + q * rc;
+                const uint32_t* yz_of_bit[32] = {nullptr};
+                double* C = reinterpret_cast<double*>(p + 64 * nn);
+                for (int b = 0; b < 32; ++b) {
+                    const size_t t = t0 + q * 32 + b;
+                    if (t < t1) { yz_of_bit[b] = g->yz.data() + t * nw; C[b] = g->c[t]; } else C[b] = 0.0;  // +0.0 padding is exact
+                }
+                fill_nibble_tables(p, nn, nw, yz_of_bit, 32);
+            }
+            out.blobs.push_back({off, kBlobHeader + nwords * rc});
+        }
+    }
+}
+
+// tiles for a given shared-memory buffer capacity
+inline void make_sliced_tiles(const SlicedHost& h, size_t cap, std::vector<STile>& tiles) {
+    tiles.clear();
+    const size_t ra = rec_bytes_A(h.nn, h.nw), rb = rec_bytes_B(h.nn, h.nw);
+    auto add_records = [&](uint32_t kind, size_t base, size_t n_rec, size_t rec) {
+        const size_t per = std::max<size_t>(1, cap / rec);
+        for (size_t r = 0; r < n_rec; r += per) {
+            const size_t n = std::min(per, n_rec - r);
+            tiles.push_back(STile{kind, (uint32_t)n, (uint32_t)(n * rec), 0, (uint64_t)(base + r * rec)});
+        }
+    };
+    add_records(kSecA, h.off_a, h.n_rec_a, ra);
+    add_records(kSecB, h.off_b, h.n_rec_b, rb);
+    size_t i = 0;
+    while (i < h.blobs.size()) {
+        size_t bytes = 0, n = 0;
+        while (i + n < h.blobs.size() && (n == 0 || bytes + h.blobs[i + n].bytes <= cap)) { bytes += h.blobs[i + n].bytes; ++n; }
+        tiles.push_back(STile{kSecC, (uint32_t)n, (uint32_t)bytes, 0, (uint64_t)h.blobs[i].offset});
+        i += n;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ device helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int NW, int NN>
+__device__ __forceinline__ void state_nibbles(const uint32_t (&s)[NW], uint32_t (&nib)[NN]) {
+#pragma unroll
+    for (int i = 0; i < NN; ++i) {
+        const int w = (4 * i) / 32, sh = (4 * i) % 32;
+        nib[i] = w < NW ? ((s[w] >> sh) & 15u) * 4u : 0u;  // byte offset inside the 64-byte nibble row
+    }
+}
+
+template <int NN>
+__device__ __forceinline__ uint32_t parity_word(const unsigned char* __restrict__ T, const uint32_t (&nib)[NN]) {
+    uint32_t p = 0;
+#pragma unroll
+    for (int i = 0; i < NN; ++i) p ^= *reinterpret_cast<const uint32_t*>(T + i * 64 + nib[i]);
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+constexpr int kLookDense = 0, kLookHash = 1;
+
+// Accumulate H[b] * psi_table(s ^ u_b) for a batch of B groups.  All B table reads are issued before any
+// is consumed (memory-level parallelism); lanes whose H is exactly 0.0 (hamiltonian.py:363) or whose coupled
+// state leaves the sector (hamiltonian.py:328) read entry 0 / slot 0 instead — a single broadcast sector —
+// and contribute H * psi = 0 exactly, so no branch is needed.
+template <int NW, int LK, bool SEC, int B>
+__device__ __forceinline__ void emit_batch(const double (&h)[B], const uint32_t* __restrict__ U, int u_stride, const uint32_t (&s)[NW],
+                                           bool valid, const Sector& sec, const LookupView& lv, double& e_re, double& e_im) {
+    double hh[B];
+    if constexpr (LK == kLookDense) {
+        double2 p[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            uint32_t j[NW];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) j[w] = s[w] ^ U[b * u_stride + w];
+            bool on = (h[b] != 0.0) & valid;
+            if constexpr (SEC) on = on && in_sector<NW>(j, sec);
+            unsigned long long k0, k1;
+            key_words64<NW>(j, k0, k1);
+            p[b] = __ldg(lv.dense + (on ? k0 : 0ull));
+            hh[b] = SEC ? (on ? h[b] : 0.0) : h[b];  // without a sector filter "off" already means h == 0 (or an invalid lane)
+        }
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            e_re = __fma_rn(hh[b], p[b].x, e_re);
+            e_im = __fma_rn(hh[b], p[b].y, e_im);
+        }
+    } else {
+        unsigned long long k0[B], k1[B], slot[B];
+        ulonglong2 kk[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            uint32_t j[NW];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) j[w] = s[w] ^ U[b * u_stride + w];
+            bool on = (h[b] != 0.0) & valid;
+            if constexpr (SEC) on = on && in_sector<NW>(j, sec);
+            key_words64<NW>(j, k0[b], k1[b]);
+            hh[b] = on ? h[b] : 0.0;
+            slot[b] = on ? (hash_key(k0[b], k1[b]) & lv.mask) : 0ull;
+            kk[b] = __ldg(reinterpret_cast<const ulonglong2*>(lv.slots + slot[b]));
+        }
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            if (hh[b] != 0.0) {
+                while (true) {  // linear probing; load factor <= 0.5, the first probe almost always decides
+                    if (kk[b].x == k0[b] && kk[b].y == k1[b]) {
+                        const double2 p = __ldg(reinterpret_cast<const double2*>(lv.slots + slot[b]) + 1);
+                        e_re = __fma_rn(hh[b], p.x, e_re);
+                        e_im = __fma_rn(hh[b], p.y, e_im);
+                        break;
+                    }
+                    if (kk[b].x == kEmptyKey && kk[b].y == kEmptyKey) break;
+                    slot[b] = (slot[b] + 1) & lv.mask;
+                    kk[b] = __ldg(reinterpret_cast<const ulonglong2*>(lv.slots + slot[b]));
+                }
+            }
+        }
+    }
+}
+
+// One state per thread.  Each CTA owns state blocks blockIdx.x, blockIdx.x + gridDim.x, ... and walks the
+// tiles [tile_lo, tile_hi) of its chunk (blockIdx.y) for each of them; with a single tile the table stays
+// resident in shared memory for the CTA's lifetime.
+template <int NW, int NN, int THREADS, int LK, bool SEC>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
+eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, Sector sec, LookupView lv,
+                   const uint64_t* __restrict__ states, const void* __restrict__ psi, int psi_dtype, int64_t M,
+                   double2* __restrict__ out, double2* __restrict__ partial) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t mbar[2];
+    constexpr int REC_A = 64 * NN + 32 * NW + 1024, REC_B = 64 * NN + 32 * NW + 2560, REC_C = 64 * NN + 256;
+
+    const int tile_lo = blockIdx.y * tiles_per_chunk;
+    const int tile_hi = min(sv.n_tiles, tile_lo + tiles_per_chunk);
+    const bool resident = (tile_hi - tile_lo) <= 1;
+    if (threadIdx.x == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t phase0 = 0, phase1 = 0;
+    bool have_resident = false;
+
+    auto issue = [&](int t, int b) {  // thread 0 only
+        const STile tl = sv.tiles[t];
+        mbar_expect_tx(&mbar[b], tl.bytes);
+        bulk_g2s(smem + (size_t)b * buf_bytes, sv.stream + tl.offset, tl.bytes, &mbar[b]);
+    };
+
+    const int64_t n_blocks = (M + THREADS - 1) / THREADS;
+    for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const int64_t m = blk * THREADS + threadIdx.x;
+        const bool valid = m < M;
+        uint32_t s[NW];
+        if (valid) load_key<NW>(states, m, s);
+        else {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) s[w] = 0;
+        }
+        uint32_t nib[NN];
+        state_nibbles<NW, NN>(s, nib);
+        double e_re = 0.0, e_im = 0.0, acc = 0.0;
+        uint32_t flip = 0;  // sign currently folded into acc (bit 31): acc holds (-1)^flip * partial sum
+
+        auto process = [&](const unsigned char* __restrict__ buf, const STile& tl) {
+            if (tl.kind == kSecA) {
+                for (uint32_t r = 0; r < tl.count; ++r) {
+                    const unsigned char* rec = buf + (size_t)r * REC_A;
+                    const uint32_t P = parity_word<NN>(rec, nib);
+                    const uint32_t* U = reinterpret_cast<const uint32_t*>(rec + 64 * NN);
+                    const unsigned char* L = rec + 64 * NN + 32 * NW;
+#pragma unroll
+                    for (int j0 = 0; j0 < 8; j0 += 4) {
+                        double h[4];
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j = j0 + jj;
+                            const uint32_t off = j == 0 ? ((P << 3) & 0x78u) : ((P >> (4 * j - 3)) & 0x78u);
+                            h[jj] = *reinterpret_cast<const double*>(L + j * 128 + off);
+                        }
+                        emit_batch<NW, LK, SEC, 4>(h, U + j0 * NW, NW, s, valid, sec, lv, e_re, e_im);
+                    }
+                }
+            } else if (tl.kind == kSecB) {
+                for (uint32_t r = 0; r < tl.count; ++r) {
+                    const unsigned char* rec = buf + (size_t)r * REC_B;
+                    const uint32_t P = parity_word<NN>(rec, nib);
+                    const uint32_t* U = reinterpret_cast<const uint32_t*>(rec + 64 * NN);
+                    const unsigned char* L = rec + 64 * NN + 32 * NW;
+                    double h[5];
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        const uint32_t off = j == 0 ? ((P << 3) & 0x1f8u) : ((P >> (6 * j - 3)) & 0x1f8u);
+                        h[j] = *reinterpret_cast<const double*>(L + j * 512 + off);
+                    }
+                    emit_batch<NW, LK, SEC, 5>(h, U, NW, s, valid, sec, lv, e_re, e_im);
+                }
+            } else {
+                const unsigned char* p = buf;
+                for (uint32_t b = 0; b < tl.count; ++b) {
+                    const uint32_t* hdr = reinterpret_cast<const uint32_t*>(p);
+                    const uint32_t n_words = hdr[0], n_sub8 = hdr[1], flags = hdr[2];
+                    if (flags & kBlobFirst) { acc = 0.0; flip = 0; }
+                    const unsigned char* rec = p + kBlobHeader;
+                    for (uint32_t q = 0; q < n_words; ++q, rec += REC_C) {
+                        const uint32_t P = parity_word<NN>(rec, nib);
+                        // acc carries the sign of the previous term; D marks where the sign changes between
+                        // consecutive terms, so each term costs shift + XOR (on acc's high word) + DADD:
+                        //   (-1)^f (x) + c  ==  (-1)^f (x + (-1)^f c)
+                        const uint32_t D = P ^ ((P << 1) | (flip >> 31));
+                        flip = P & 0x80000000u;
+                        const double* C = reinterpret_cast<const double*>(rec + 64 * NN);
+                        const uint32_t nsb = min(4u, n_sub8 - 4u * q);
+                        for (uint32_t sb = 0; sb < nsb; ++sb) {
+                            const uint32_t Db = D >> (8 * sb);
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) {
+                                const int hi = __double2hiint(acc) ^ (int)((Db << (31 - t)) & 0x80000000u);
+                                acc = __dadd_rn(__hiloint2double(hi, __double2loint(acc)), C[sb * 8 + t]);
+                            }
+                        }
+                        if (nsb < 4) flip = (P << (8 * (4 - nsb))) & 0x80000000u;  // sign of the last processed term
+                    }
+                    if (flags & kBlobLast) {
+                        double h[1] = {__hiloint2double(__double2hiint(acc) ^ (int)flip, __double2loint(acc))};
+                        emit_batch<NW, LK, SEC, 1>(h, hdr + 4, NW, s, valid, sec, lv, e_re, e_im);
+                    }
+                    p += kBlobHeader + (size_t)n_words * REC_C;
+                }
+            }
+        };
+
+        if (threadIdx.x == 0 && tile_lo < tile_hi && !(resident && have_resident)) issue(tile_lo, 0);
+        for (int t = tile_lo; t < tile_hi; ++t) {
+            const int b = resident ? 0 : ((t - tile_lo) & 1);
+            if (!resident && threadIdx.x == 0 && t + 1 < tile_hi) issue(t + 1, b ^ 1);
+            if (!(resident && have_resident)) {
+                if (b == 0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1; }
+                else        { mbar_wait(&mbar[1], phase1); phase1 ^= 1; }
+            }
+            have_resident = resident;
+            process(smem + (size_t)b * buf_bytes, sv.tiles[t]);
+            if (!resident) __syncthreads();  // every thread is done with buffer b before it is refilled
+        }
+
+        if (valid) {
+            if (partial) partial[(int64_t)blockIdx.y * M + m] = make_double2(e_re, e_im);
+            else out[m] = div_conj(make_double2(e_re, e_im), load_psi(psi, psi_dtype, m));
+        }
+    }
+}
+
+// sum the per-chunk partial sums in chunk order, divide by psi(s) and conjugate (energy.py:248)
+__global__ void eloc_finalize_kernel(const double2* __restrict__ partial, int n_chunks, const void* __restrict__ psi, int psi_dtype,
+                                     int64_t M, double2* __restrict__ out) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    double re = 0.0, im = 0.0;
+    for (int c = 0; c < n_chunks; ++c) {
+        const double2 p = partial[(int64_t)c * M + m];
+        re = __dadd_rn(re, p.x); im = __dadd_rn(im, p.y);
+    }
+    out[m] = div_conj(make_double2(re, im), load_psi(psi, psi_dtype, m));
+}
+
+}  // namespace naqs

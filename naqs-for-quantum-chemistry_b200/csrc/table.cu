@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "eloc_kernels.cuh"
+#include "sliced.cuh"
 
 namespace naqs {
 
@@ -77,6 +78,11 @@ __global__ void dense_scatter_kernel(double2* dense, const uint64_t* __restrict_
 
 // ------------------------------------------------------------------------------------------ launch helpers
 constexpr int kThreads = 256;
+
+// sliced kernel launch shapes: threads per CTA and shared-memory tile capacity (two buffers per CTA)
+constexpr int kSlicedThreads[3] = {1024, 512, 256};
+constexpr size_t kSlicedCap[3] = {112640, 55296, 26624};
+constexpr size_t kSlicedMaxBlob = 24576;
 
 static int tile_cap_for(int nw32, int64_t K) {
     // keep a tile <= ~56 KB so four CTAs of 256 threads fit one SM; whole table in one tile when it fits
@@ -174,6 +180,28 @@ int naqs_table_create(naqs_table_t** out, const uint64_t* h_xy, const uint64_t* 
     }
     t->n_tiles = (int)tiles.size();
 
+    // sliced (v2) stream: groups in ascending-XY order with their terms in reference order
+    SlicedHost sh;
+    std::vector<STile> stiles[3];
+    {
+        std::vector<HostGroup> hg((size_t)G);
+        for (int64_t g = 0; g < G; ++g) {
+            HostGroup& x = hg[(size_t)g];
+            for (int w = 0; w < 4; ++w) x.u[w] = w < NW ? gxy[(size_t)w * G + g] : 0u;
+            const uint32_t b = gstart[(size_t)g], e = gstart[(size_t)g + 1];
+            x.yz.resize((size_t)(e - b) * NW);
+            x.c.assign(coeff.begin() + b, coeff.begin() + e);
+            for (uint32_t i = b; i < e; ++i)
+                for (int w = 0; w < NW; ++w) x.yz[(size_t)(i - b) * NW + w] = yz[(size_t)w * K + i];
+        }
+        build_sliced_host(hg, n_qubits, NW, kSlicedMaxBlob, sh);
+        for (int c = 0; c < 3; ++c) make_sliced_tiles(sh, kSlicedCap[c], stiles[c]);
+        t->nn = sh.nn;
+        t->stream_bytes = sh.stream.size();
+    }
+    const char* algo_env = getenv("NAQS_ELOC_ALGO");
+    t->algo = (algo_env && std::string(algo_env) == "direct") ? 1 : 0;
+
     int rc = NAQS_OK;
     auto upload = [&](void** dptr, const void* src, size_t bytes) -> int {
         NAQS_CUDA(cudaMalloc(dptr, std::max<size_t>(bytes, 16)));
@@ -184,10 +212,15 @@ int naqs_table_create(naqs_table_t** out, const uint64_t* h_xy, const uint64_t* 
         (rc = upload((void**)&t->d_coeff, coeff.data(), (size_t)K * 8)) ||
         (rc = upload((void**)&t->d_gxy, gxy.data(), (size_t)NW * G * 4)) ||
         (rc = upload((void**)&t->d_gstart, gstart.data(), (size_t)(G + 1) * 4)) ||
-        (rc = upload((void**)&t->d_tiles, tiles.data(), tiles.size() * sizeof(Tile)))) {
+        (rc = upload((void**)&t->d_tiles, tiles.data(), tiles.size() * sizeof(Tile))) ||
+        (rc = upload((void**)&t->d_stream, sh.stream.data(), sh.stream.size())) ||
+        (rc = upload(&t->d_stiles[0], stiles[0].data(), stiles[0].size() * sizeof(STile))) ||
+        (rc = upload(&t->d_stiles[1], stiles[1].data(), stiles[1].size() * sizeof(STile))) ||
+        (rc = upload(&t->d_stiles[2], stiles[2].data(), stiles[2].size() * sizeof(STile)))) {
         naqs_table_destroy(t);
         return rc;
     }
+    for (int c = 0; c < 3; ++c) t->n_stiles[c] = (int)stiles[c].size();
     if (cudaStreamCreateWithFlags(&t->own_stream, cudaStreamNonBlocking) != cudaSuccess) t->own_stream = nullptr;
     *out = t;
     return NAQS_OK;
@@ -200,7 +233,8 @@ int naqs_table_destroy(naqs_table_t* t) {
     cudaFree(t->d_dense); cudaFree(t->d_slots); cudaFree(t->d_ws); cudaFree(t->d_stage);
     if (t->h_pinned) cudaFreeHost(t->h_pinned);
     if (t->own_stream) cudaStreamDestroy(t->own_stream);
-    cudaFree(t->d_tiles); cudaFree(t->d_binom);
+    cudaFree(t->d_tiles); cudaFree(t->d_binom); cudaFree(t->d_stream); cudaFree(t->d_partial);
+    for (int c = 0; c < 3; ++c) cudaFree(t->d_stiles[c]);
     delete t;
     return NAQS_OK;
 }
@@ -275,7 +309,95 @@ static int launch_eloc(naqs_table_t* t, const uint64_t* d_states, const void* d_
     return NAQS_OK;
 }
 
+template <int NW, int NN, int CFG, int LK, bool SEC>
+static int launch_sliced_cfg(naqs_table_t* t, const uint64_t* d_states, const void* d_psi, int psi_dtype, int64_t M,
+                             double* d_eloc, cudaStream_t stream, int n_chunks, int sm_count) {
+    constexpr int THREADS = kSlicedThreads[CFG];
+    const int n_tiles = t->n_stiles[CFG];
+    const int tiles_per_chunk = std::max(1, (n_tiles + n_chunks - 1) / n_chunks);
+    n_chunks = std::max(1, (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk);
+    const size_t cap = kSlicedCap[CFG];
+    const bool resident = tiles_per_chunk <= 1;
+    const size_t smem = resident ? cap : 2 * cap;
+    auto kern = eloc_sliced_kernel<NW, NN, THREADS, LK, SEC>;
+    NAQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * cap)));
+    double2* partial = nullptr;
+    if (n_chunks > 1) {
+        const size_t need = (size_t)n_chunks * M * sizeof(double2);
+        if (t->partial_bytes < need) {
+            cudaFree(t->d_partial); t->d_partial = nullptr; t->partial_bytes = 0;
+            NAQS_CUDA(cudaMalloc((void**)&t->d_partial, need));
+            t->partial_bytes = need;
+        }
+        partial = t->d_partial;
+    }
+    const int64_t n_blocks = (M + THREADS - 1) / THREADS;
+    const int slots = sm_count * (1024 / THREADS);
+    dim3 grid((unsigned)std::min<int64_t>(n_blocks, slots), (unsigned)n_chunks);
+    SlicedView sv{t->d_stream, (const STile*)t->d_stiles[CFG], n_tiles, t->nn};
+    kern<<<grid, THREADS, smem, stream>>>(sv, tiles_per_chunk, (uint32_t)cap, t->sector, t->lookup(), d_states, d_psi, psi_dtype, M,
+                                          reinterpret_cast<double2*>(d_eloc), partial);
+    NAQS_LAUNCHED();
+    if (n_chunks > 1) {
+        eloc_finalize_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(partial, n_chunks, d_psi, psi_dtype, M,
+                                                                            reinterpret_cast<double2*>(d_eloc));
+        NAQS_LAUNCHED();
+    }
+    return NAQS_OK;
+}
+
+template <int NW, int NN>
+static int launch_sliced(naqs_table_t* t, const uint64_t* d_states, const void* d_psi, int psi_dtype, int64_t M, double* d_eloc,
+                         cudaStream_t stream) {
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, t->device);
+    // pick the launch shape: large CTAs when there are at least two waves of them, else smaller CTAs, and split the
+    // table into chunks (grid.y) when even those cannot fill the machine
+    int cfg = 2;
+    for (int c = 0; c < 3; ++c) {
+        const int64_t n_blocks = (M + kSlicedThreads[c] - 1) / kSlicedThreads[c];
+        if (n_blocks >= 2ll * sm_count * (1024 / kSlicedThreads[c])) { cfg = c; break; }
+    }
+    int n_chunks = 1;
+    {
+        const int64_t n_blocks = (M + kSlicedThreads[cfg] - 1) / kSlicedThreads[cfg];
+        const int64_t slots = (int64_t)sm_count * (1024 / kSlicedThreads[cfg]);
+        if (n_blocks < slots) {
+            double best = -1.0;
+            const int max_chunks = std::min(t->n_stiles[cfg], 16);
+            for (int ch = 1; ch <= max_chunks; ++ch) {
+                const int64_t ctas = n_blocks * ch, waves = (ctas + slots - 1) / slots;
+                const double eff = (double)ctas / (double)(waves * slots) - 0.01 * ch;  // mild preference for fewer chunks
+                if (eff > best) { best = eff; n_chunks = ch; }
+            }
+        }
+    }
+#define NAQS_SL(CFG, LK, SEC) launch_sliced_cfg<NW, NN, CFG, LK, SEC>(t, d_states, d_psi, psi_dtype, M, d_eloc, stream, n_chunks, sm_count)
+    const bool hash = t->lookup_kind == NAQS_LOOKUP_HASH, secf = t->sector.enabled != 0;
+    switch (cfg * 4 + (hash ? 2 : 0) + (secf ? 1 : 0)) {
+        case 0: return NAQS_SL(0, kLookDense, false);
+        case 1: return NAQS_SL(0, kLookDense, true);
+        case 2: return NAQS_SL(0, kLookHash, false);
+        case 3: return NAQS_SL(0, kLookHash, true);
+        case 4: return NAQS_SL(1, kLookDense, false);
+        case 5: return NAQS_SL(1, kLookDense, true);
+        case 6: return NAQS_SL(1, kLookHash, false);
+        case 7: return NAQS_SL(1, kLookHash, true);
+        case 8: return NAQS_SL(2, kLookDense, false);
+        case 9: return NAQS_SL(2, kLookDense, true);
+        case 10: return NAQS_SL(2, kLookHash, false);
+        default: return NAQS_SL(2, kLookHash, true);
+    }
+#undef NAQS_SL
+}
+
 extern "C" {
+
+int naqs_table_set_algo(naqs_table_t* t, int algo) {
+    NAQS_REQUIRE(t && (algo == 0 || algo == 1), NAQS_ERR_ARG, "naqs_table_set_algo: algo must be 0 (sliced) or 1 (direct)");
+    t->algo = algo;
+    return NAQS_OK;
+}
 
 int naqs_eloc(naqs_table_t* t, const uint64_t* d_states, const void* d_psi, int psi_dtype, int64_t M, double* d_eloc,
               void* stream_) {
@@ -287,6 +409,14 @@ int naqs_eloc(naqs_table_t* t, const uint64_t* d_states, const void* d_psi, int 
     if (M == 0) return NAQS_OK;
     DeviceGuard guard(t->device);
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (t->algo == 0) {
+        switch (t->nn) {
+            case 5: return launch_sliced<1, 5>(t, d_states, d_psi, psi_dtype, M, d_eloc, stream);
+            case 8: return launch_sliced<1, 8>(t, d_states, d_psi, psi_dtype, M, d_eloc, stream);
+            case 16: return launch_sliced<2, 16>(t, d_states, d_psi, psi_dtype, M, d_eloc, stream);
+            default: return launch_sliced<4, 32>(t, d_states, d_psi, psi_dtype, M, d_eloc, stream);
+        }
+    }
     switch (t->nw32) {
         case 1: return launch_eloc<1>(t, d_states, d_psi, psi_dtype, M, d_eloc, stream);
         case 2: return launch_eloc<2>(t, d_states, d_psi, psi_dtype, M, d_eloc, stream);

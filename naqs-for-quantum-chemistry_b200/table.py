@@ -48,6 +48,13 @@ class DeviceTermTable:
         except Exception:  # noqa: BLE001  (interpreter shutdown)
             pass
 
+    def set_algo(self, algo):
+        """Kernel formulation of the fused path: "sliced" (nibble-sliced parity + group LUT, default) or "direct"
+        (AND/POPC walk).  Both accumulate every H_ij in reference order; they differ only in speed."""
+        code = {"sliced": 0, "direct": 1}[algo]
+        _lib.check(_lib.load().naqs_table_set_algo(self._h, code), "naqs_table_set_algo")
+        return self
+
     # ------------------------------------------------------------------ helpers
     def _keys(self, x):
         return _lib.keys_to_device(x, self.words, self.device)

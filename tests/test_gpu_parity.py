@@ -93,6 +93,29 @@ def test_rows_match_reference_csr_bit_exact(name):
     assert np.array_equal(np.sort(t.restricted_index(uniq.view(np.int64)).cpu().numpy()), case["coupled_unique_restricted"])
 
 
+@pytest.mark.parametrize("mol,sector,m", [("LiH", True, 225), ("N2", True, 6000), ("N2", False, 50000), ("Li2O", True, 4000), ("H2S", True, 2000)])
+def test_direct_and_sliced_formulations_agree(mol, sector, m):
+    """The two kernel formulations (AND/POPC walk vs nibble-sliced parity + group LUT) produce the same E_loc; both are
+    checked against the oracle, at sizes that exercise every launch shape (1024/512/256-thread CTAs, table chunks)."""
+    nb200, c_oracle, eo = _mods()
+    t, ct, (N, na, nb) = make_tables(mol, sector)
+    if sector:
+        st = random_sector_states(N, na, nb, min(m, eo.comb((N + 1) // 2, na) * eo.comb(N // 2, nb)), seed=31)
+    else:
+        st = random_keys(N, m, seed=32)
+    psi = eo.synthetic_psi(len(st), seed=33)
+    ref = ct.local_energy(st, psi)
+    out = {}
+    for algo in ("sliced", "direct"):
+        t.set_algo(algo)
+        for kind in (nb200._lib.LOOKUP_HASH, nb200._lib.LOOKUP_DENSE) if N <= 22 else (nb200._lib.LOOKUP_HASH,):
+            e = gpu_eloc(t, st, psi, kind=kind)
+            assert rel_err(e, ref).max() <= ELOC_RTOL, (algo, kind)
+            out[(algo, kind)] = e
+    a, b = out[("sliced", nb200._lib.LOOKUP_HASH)], out[("direct", nb200._lib.LOOKUP_HASH)]
+    assert rel_err(a, b).max() <= 1e-13
+
+
 # ------------------------------------------------------------------------------------------- oracle, seeded
 @pytest.mark.parametrize("mol,m,sector", [("LiH", 225, True), ("H2O", 441, True), ("NH3", 3136, True), ("N2", 14400, True),
                                           ("N2_2.25", 5000, True), ("C2", 8000, True), ("H2S", 3000, True), ("Li2O", 3000, True),
