@@ -93,14 +93,24 @@ struct LookupView {
     const HashSlot* slots;   // [cap]  (kind HASH)
     unsigned long long mask; // cap - 1
     int kind;
+    int shift;               // 32 - log2(cap): slot = hash32 >> shift
 };
 
 __host__ __device__ inline unsigned long long mix64(unsigned long long x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
     return x;
 }
-__host__ __device__ inline unsigned long long hash_key(unsigned long long k0, unsigned long long k1) {
-    return mix64(k0 ^ (k1 * 0x9E3779B97F4A7C15ULL));
+// 32-bit multiplicative hash of a (up to 128-bit) key, a handful of IMAD/SHF/LOP3: the probe sequence starts at
+// hash32 >> shift.  Table capacities are powers of two <= 2^31 with load factor <= 0.5.
+__host__ __device__ inline uint32_t hash32(unsigned long long k0, unsigned long long k1) {
+    uint32_t h = (uint32_t)k0 * 0x9E3779B1u + (uint32_t)(k0 >> 32) * 0x85EBCA6Bu + (uint32_t)k1 * 0xC2B2AE35u +
+                 (uint32_t)(k1 >> 32) * 0x27D4EB2Fu;
+    h = (h ^ (h >> 15)) * 0x2C1B3C6Du;
+    h ^= h >> 13;
+    return h * 0x297A2D39u;
+}
+__host__ __device__ inline unsigned long long hash_slot(unsigned long long k0, unsigned long long k1, int shift) {
+    return (unsigned long long)(hash32(k0, k1) >> shift);
 }
 
 }  // namespace naqs
@@ -121,8 +131,8 @@ struct naqs_table {
     int algo = 0;                  // 0 = sliced (default), 1 = direct
     unsigned char* d_stream = nullptr;
     size_t stream_bytes = 0;
-    void* d_stiles[3] = {nullptr, nullptr, nullptr};
-    int n_stiles[3] = {0, 0, 0};
+    void* d_stiles[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [0..2] dense, [3..5] hash tile lists
+    int n_stiles[6] = {0, 0, 0, 0, 0, 0};
     int nn = 0;
     double2* d_partial = nullptr;
     size_t partial_bytes = 0;
@@ -144,7 +154,9 @@ struct naqs_table {
 
     naqs::TableView view() const { return naqs::TableView{d_yz, d_coeff, d_gxy, d_gstart, (int)K, (int)G}; }
     naqs::LookupView lookup() const {
-        return naqs::LookupView{d_dense, d_slots, (unsigned long long)(hash_cap - 1), lookup_kind};
+        int shift = 32;
+        for (int64_t c = hash_cap; c > 1; c >>= 1) --shift;
+        return naqs::LookupView{d_dense, d_slots, (unsigned long long)(hash_cap - 1), lookup_kind, shift};
     }
 };
 

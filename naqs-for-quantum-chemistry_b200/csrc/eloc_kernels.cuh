@@ -61,7 +61,7 @@ __device__ __forceinline__ double2 lookup_psi(const LookupView& lv, const uint32
     if (lv.kind == NAQS_LOOKUP_DENSE) {
         return __ldg(lv.dense + k0);
     }
-    unsigned long long h = hash_key(k0, k1) & lv.mask;
+    unsigned long long h = hash_slot(k0, k1, lv.shift);
     while (true) {
         const HashSlot* sl = lv.slots + h;
         const ulonglong2 kk = __ldg(reinterpret_cast<const ulonglong2*>(sl));

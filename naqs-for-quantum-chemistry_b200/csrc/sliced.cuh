@@ -223,11 +223,11 @@ constexpr int kLookDense = 0, kLookHash = 1;
 // is consumed (memory-level parallelism); lanes whose H is exactly 0.0 (hamiltonian.py:363) or whose coupled
 // state leaves the sector (hamiltonian.py:328) read entry 0 / slot 0 instead — a single broadcast sector —
 // and contribute H * psi = 0 exactly, so no branch is needed.
-template <int NW, int LK, bool SEC, int B>
+template <int NW, bool SEC, bool KEYORDER, int B>
 __device__ __forceinline__ void emit_batch(const double (&h)[B], const uint32_t* __restrict__ U, int u_stride, const uint32_t (&s)[NW],
                                            bool valid, const Sector& sec, const LookupView& lv, double& e_re, double& e_im) {
     double hh[B];
-    if constexpr (LK == kLookDense) {
+    {
         double2 p[B];
 #pragma unroll
         for (int b = 0; b < B; ++b) {
@@ -238,7 +238,9 @@ __device__ __forceinline__ void emit_batch(const double (&h)[B], const uint32_t*
             if constexpr (SEC) on = on && in_sector<NW>(j, sec);
             unsigned long long k0, k1;
             key_words64<NW>(j, k0, k1);
-            p[b] = __ldg(lv.dense + (on ? k0 : 0ull));
+            // key-order mode: the 32 lanes hold 32 consecutive keys, so s ^ u stays inside one aligned 32-entry block of
+            // the table for every lane — loading it even where h == 0 costs no extra line, and needs no select
+            p[b] = __ldg(lv.dense + ((KEYORDER || on) ? k0 : 0ull));
             hh[b] = SEC ? (on ? h[b] : 0.0) : h[b];  // without a sector filter "off" already means h == 0 (or an invalid lane)
         }
 #pragma unroll
@@ -246,48 +248,53 @@ __device__ __forceinline__ void emit_batch(const double (&h)[B], const uint32_t*
             e_re = __fma_rn(hh[b], p[b].x, e_re);
             e_im = __fma_rn(hh[b], p[b].y, e_im);
         }
-    } else {
-        unsigned long long k0[B], k1[B], slot[B];
-        ulonglong2 kk[B];
-#pragma unroll
-        for (int b = 0; b < B; ++b) {
-            uint32_t j[NW];
-#pragma unroll
-            for (int w = 0; w < NW; ++w) j[w] = s[w] ^ U[b * u_stride + w];
-            bool on = (h[b] != 0.0) & valid;
-            if constexpr (SEC) on = on && in_sector<NW>(j, sec);
-            key_words64<NW>(j, k0[b], k1[b]);
-            hh[b] = on ? h[b] : 0.0;
-            slot[b] = on ? (hash_key(k0[b], k1[b]) & lv.mask) : 0ull;
-            kk[b] = __ldg(reinterpret_cast<const ulonglong2*>(lv.slots + slot[b]));
-        }
-#pragma unroll
-        for (int b = 0; b < B; ++b) {
-            if (hh[b] != 0.0) {
-                while (true) {  // linear probing; load factor <= 0.5, the first probe almost always decides
-                    if (kk[b].x == k0[b] && kk[b].y == k1[b]) {
-                        const double2 p = __ldg(reinterpret_cast<const double2*>(lv.slots + slot[b]) + 1);
-                        e_re = __fma_rn(hh[b], p.x, e_re);
-                        e_im = __fma_rn(hh[b], p.y, e_im);
-                        break;
-                    }
-                    if (kk[b].x == kEmptyKey && kk[b].y == kEmptyKey) break;
-                    slot[b] = (slot[b] + 1) & lv.mask;
-                    kk[b] = __ldg(reinterpret_cast<const ulonglong2*>(lv.slots + slot[b]));
-                }
-            }
-        }
     }
 }
+
+// Hash-lookup ("heavy") epilogue of one coupling: sector filter (hamiltonian.py:328), probe of the 32-byte-slot hash
+// table, complex multiply-add.  Called only for couplings whose H is not exactly 0.0 (hamiltonian.py:363), which the
+// per-thread queue of the kernel below makes dense across the warp.
+template <int NW, bool SEC>
+__device__ __forceinline__ void heavy_lookup(double h, const uint32_t* __restrict__ u, const uint32_t (&s)[NW], const Sector& sec,
+                                             const LookupView& lv, double& e_re, double& e_im) {
+    uint32_t j[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) j[w] = s[w] ^ u[w];
+    if constexpr (SEC) {
+        if (!in_sector<NW>(j, sec)) return;
+    }
+    unsigned long long k0, k1;
+    key_words64<NW>(j, k0, k1);
+    unsigned long long slot = hash_slot(k0, k1, lv.shift);
+    while (true) {  // linear probing; load factor <= 0.5, the first probe almost always decides
+        const HashSlot* sl = lv.slots + slot;
+        const ulonglong2 kk = __ldg(reinterpret_cast<const ulonglong2*>(sl));
+        if (kk.x == k0 && kk.y == k1) {
+            const double2 p = __ldg(reinterpret_cast<const double2*>(sl) + 1);
+            e_re = __fma_rn(h, p.x, e_re);
+            e_im = __fma_rn(h, p.y, e_im);
+            return;
+        }
+        if (kk.x == kEmptyKey && kk.y == kEmptyKey) return;
+        slot = (slot + 1) & lv.mask;
+    }
+}
+
+constexpr int kQueueCap = 16;  // pending couplings per thread (hash mode)
 
 // One state per thread.  Each CTA owns state blocks blockIdx.x, blockIdx.x + gridDim.x, ... and walks the
 // tiles [tile_lo, tile_hi) of its chunk (blockIdx.y) for each of them; with a single tile the table stays
 // resident in shared memory for the CTA's lifetime.
-template <int NW, int NN, int THREADS, int LK, bool SEC>
+//
+// KEYORDER (dense lookup, batch dense in key space): thread m IS key m (states == nullptr, M = 2^N); `need` is a bitmap
+// of the keys that occur as rows; the raw sums S[k] = sum_u H[k, k^u] psi(k^u) go to partial[chunk * M + k] and
+// eloc_rows_finalize_kernel turns them into E_loc per row.  A warp then holds 32 consecutive keys and every table
+// read of a group falls into one aligned 512-byte block: 4 L1 lines per request instead of ~11 scattered sectors.
+template <int NW, int NN, int THREADS, int LK, bool SEC, bool KEYORDER>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
-eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, Sector sec, LookupView lv,
-                   const uint64_t* __restrict__ states, const void* __restrict__ psi, int psi_dtype, int64_t M,
-                   double2* __restrict__ out, double2* __restrict__ partial) {
+eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint32_t queue_offset, Sector sec, LookupView lv,
+                   const uint64_t* __restrict__ states, const uint32_t* __restrict__ need, const void* __restrict__ psi,
+                   int psi_dtype, int64_t M, double2* __restrict__ out, double2* __restrict__ partial) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t mbar[2];
     constexpr int REC_A = 64 * NN + 32 * NW + 1024, REC_B = 64 * NN + 32 * NW + 2560, REC_C = 64 * NN + 256;
@@ -313,17 +320,45 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, Secto
     const int64_t n_blocks = (M + THREADS - 1) / THREADS;
     for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
         const int64_t m = blk * THREADS + threadIdx.x;
-        const bool valid = m < M;
+        bool valid = m < M;
         uint32_t s[NW];
-        if (valid) load_key<NW>(states, m, s);
-        else {
+        if constexpr (KEYORDER) {
+            s[0] = (uint32_t)m;
 #pragma unroll
-            for (int w = 0; w < NW; ++w) s[w] = 0;
+            for (int w = 1; w < NW; ++w) s[w] = 0;
+            valid = valid && ((need[m >> 5] >> (m & 31)) & 1u);
+        } else {
+            if (valid) load_key<NW>(states, m, s);
+            else {
+#pragma unroll
+                for (int w = 0; w < NW; ++w) s[w] = 0;
+            }
         }
         uint32_t nib[NN];
         state_nibbles<NW, NN>(s, nib);
         double e_re = 0.0, e_im = 0.0, acc = 0.0;
         uint32_t flip = 0;  // sign currently folded into acc (bit 31): acc holds (-1)^flip * partial sum
+
+        // hash mode: couplings with H != 0 are parked in a per-thread queue (shared memory, [slot][thread] layout, one
+        // 32-bit word each: LUT entry offset | flip-mask offset inside the current tile) and resolved in warp-wide
+        // rounds, so the expensive part (sector test, hashing, probing) runs with most lanes busy although only a
+        // fraction of the (state, group) pairs couples.  The queue is drained before a tile buffer is released.
+        uint32_t qcnt = 0;
+        uint32_t* const q = reinterpret_cast<uint32_t*>(smem + queue_offset) + threadIdx.x;
+        auto pop_round = [&](const unsigned char* __restrict__ buf) {
+            if (qcnt > 0) {
+                --qcnt;
+                const uint32_t e = q[qcnt * THREADS];
+                heavy_lookup<NW, SEC>(*reinterpret_cast<const double*>(buf + (e & 0xffffu) * 8u),
+                                      reinterpret_cast<const uint32_t*>(buf + (e >> 16) * 4u), s, sec, lv, e_re, e_im);
+            }
+        };
+        auto push = [&](double h, const unsigned char* __restrict__ buf, const unsigned char* lut_entry, const uint32_t* u) {
+            if (h != 0.0 && valid) {
+                q[qcnt * THREADS] = (uint32_t)((lut_entry - buf) >> 3) | ((uint32_t)((reinterpret_cast<const unsigned char*>(u) - buf) >> 2) << 16);
+                ++qcnt;
+            }
+        };
 
         auto process = [&](const unsigned char* __restrict__ buf, const STile& tl) {
             if (tl.kind == kSecA) {
@@ -332,16 +367,26 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, Secto
                     const uint32_t P = parity_word<NN>(rec, nib);
                     const uint32_t* U = reinterpret_cast<const uint32_t*>(rec + 64 * NN);
                     const unsigned char* L = rec + 64 * NN + 32 * NW;
+                    if constexpr (LK == kLookDense) {
 #pragma unroll
-                    for (int j0 = 0; j0 < 8; j0 += 4) {
-                        double h[4];
+                        for (int j0 = 0; j0 < 8; j0 += 4) {
+                            double h[4];
 #pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {
-                            const int j = j0 + jj;
-                            const uint32_t off = j == 0 ? ((P << 3) & 0x78u) : ((P >> (4 * j - 3)) & 0x78u);
-                            h[jj] = *reinterpret_cast<const double*>(L + j * 128 + off);
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const int j = j0 + jj;
+                                const uint32_t off = j == 0 ? ((P << 3) & 0x78u) : ((P >> (4 * j - 3)) & 0x78u);
+                                h[jj] = *reinterpret_cast<const double*>(L + j * 128 + off);
+                            }
+                            emit_batch<NW, SEC, KEYORDER, 4>(h, U + j0 * NW, NW, s, valid, sec, lv, e_re, e_im);
                         }
-                        emit_batch<NW, LK, SEC, 4>(h, U + j0 * NW, NW, s, valid, sec, lv, e_re, e_im);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint32_t off = j == 0 ? ((P << 3) & 0x78u) : ((P >> (4 * j - 3)) & 0x78u);
+                            const unsigned char* le = L + j * 128 + off;
+                            push(*reinterpret_cast<const double*>(le), buf, le, U + j * NW);
+                        }
+                        while (__any_sync(0xffffffffu, qcnt > kQueueCap - 8)) pop_round(buf);
                     }
                 }
             } else if (tl.kind == kSecB) {
@@ -350,13 +395,23 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, Secto
                     const uint32_t P = parity_word<NN>(rec, nib);
                     const uint32_t* U = reinterpret_cast<const uint32_t*>(rec + 64 * NN);
                     const unsigned char* L = rec + 64 * NN + 32 * NW;
-                    double h[5];
+                    if constexpr (LK == kLookDense) {
+                        double h[5];
 #pragma unroll
-                    for (int j = 0; j < 5; ++j) {
-                        const uint32_t off = j == 0 ? ((P << 3) & 0x1f8u) : ((P >> (6 * j - 3)) & 0x1f8u);
-                        h[j] = *reinterpret_cast<const double*>(L + j * 512 + off);
+                        for (int j = 0; j < 5; ++j) {
+                            const uint32_t off = j == 0 ? ((P << 3) & 0x1f8u) : ((P >> (6 * j - 3)) & 0x1f8u);
+                            h[j] = *reinterpret_cast<const double*>(L + j * 512 + off);
+                        }
+                        emit_batch<NW, SEC, KEYORDER, 5>(h, U, NW, s, valid, sec, lv, e_re, e_im);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) {
+                            const uint32_t off = j == 0 ? ((P << 3) & 0x1f8u) : ((P >> (6 * j - 3)) & 0x1f8u);
+                            const unsigned char* le = L + j * 512 + off;
+                            push(*reinterpret_cast<const double*>(le), buf, le, U + j * NW);
+                        }
+                        while (__any_sync(0xffffffffu, qcnt > kQueueCap - 8)) pop_round(buf);
                     }
-                    emit_batch<NW, LK, SEC, 5>(h, U, NW, s, valid, sec, lv, e_re, e_im);
                 }
             } else {
                 const unsigned char* p = buf;
@@ -386,7 +441,8 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, Secto
                     }
                     if (flags & kBlobLast) {
                         double h[1] = {__hiloint2double(__double2hiint(acc) ^ (int)flip, __double2loint(acc))};
-                        emit_batch<NW, LK, SEC, 1>(h, hdr + 4, NW, s, valid, sec, lv, e_re, e_im);
+                        if constexpr (LK == kLookDense) emit_batch<NW, SEC, KEYORDER, 1>(h, hdr + 4, NW, s, valid, sec, lv, e_re, e_im);
+                        else if (h[0] != 0.0 && valid) heavy_lookup<NW, SEC>(h[0], hdr + 4, s, sec, lv, e_re, e_im);
                     }
                     p += kBlobHeader + (size_t)n_words * REC_C;
                 }
@@ -403,11 +459,14 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, Secto
             }
             have_resident = resident;
             process(smem + (size_t)b * buf_bytes, sv.tiles[t]);
+            if constexpr (LK == kLookHash) {
+                while (__any_sync(0xffffffffu, qcnt > 0)) pop_round(smem + (size_t)b * buf_bytes);
+            }
             if (!resident) __syncthreads();  // every thread is done with buffer b before it is refilled
         }
 
         if (valid) {
-            if (partial) partial[(int64_t)blockIdx.y * M + m] = make_double2(e_re, e_im);
+            if (KEYORDER || partial) partial[(int64_t)blockIdx.y * M + m] = make_double2(e_re, e_im);
             else out[m] = div_conj(make_double2(e_re, e_im), load_psi(psi, psi_dtype, m));
         }
     }
@@ -421,6 +480,28 @@ __global__ void eloc_finalize_kernel(const double2* __restrict__ partial, int n_
     double re = 0.0, im = 0.0;
     for (int c = 0; c < n_chunks; ++c) {
         const double2 p = partial[(int64_t)c * M + m];
+        re = __dadd_rn(re, p.x); im = __dadd_rn(im, p.y);
+    }
+    out[m] = div_conj(make_double2(re, im), load_psi(psi, psi_dtype, m));
+}
+
+// key-order mode helpers: mark the keys that occur as rows; gather S[key_m] per row, divide and conjugate
+__global__ void mark_keys_kernel(const uint64_t* __restrict__ states, int64_t M, uint32_t* __restrict__ need) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const unsigned long long k = states[m];
+    atomicOr(&need[k >> 5], 1u << (k & 31));
+}
+
+__global__ void eloc_rows_finalize_kernel(const double2* __restrict__ partial, int n_chunks, int64_t n_keys,
+                                          const uint64_t* __restrict__ states, const void* __restrict__ psi, int psi_dtype,
+                                          int64_t M, double2* __restrict__ out) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const unsigned long long k = states[m];
+    double re = 0.0, im = 0.0;
+    for (int c = 0; c < n_chunks; ++c) {
+        const double2 p = partial[(int64_t)c * n_keys + k];
         re = __dadd_rn(re, p.x); im = __dadd_rn(im, p.y);
     }
     out[m] = div_conj(make_double2(re, im), load_psi(psi, psi_dtype, m));

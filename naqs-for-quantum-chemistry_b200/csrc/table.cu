@@ -46,13 +46,13 @@ __device__ __forceinline__ ulonglong2 cas128(unsigned long long* addr, ulonglong
     return old;
 }
 
-__global__ void hash_insert_kernel(HashSlot* slots, unsigned long long mask, const uint64_t* __restrict__ keys, int words,
+__global__ void hash_insert_kernel(HashSlot* slots, unsigned long long mask, int shift, const uint64_t* __restrict__ keys, int words,
                                    const void* __restrict__ psi, int psi_dtype, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long k0 = keys[i * words], k1 = words > 1 ? keys[i * words + 1] : 0ull;
     const double2 p = load_psi(psi, psi_dtype, i);
-    unsigned long long h = hash_key(k0, k1) & mask;
+    unsigned long long h = hash_slot(k0, k1, shift);
     while (true) {
         HashSlot* sl = slots + h;
         const ulonglong2 old = cas128(sl->key, make_ulonglong2(kEmptyKey, kEmptyKey), make_ulonglong2(k0, k1));
@@ -81,8 +81,9 @@ constexpr int kThreads = 256;
 
 // sliced kernel launch shapes: threads per CTA and shared-memory tile capacity (two buffers per CTA)
 constexpr int kSlicedThreads[3] = {1024, 512, 256};
-constexpr size_t kSlicedCap[3] = {112640, 55296, 26624};
-constexpr size_t kSlicedMaxBlob = 24576;
+// tile capacities: [0..2] dense lookup, [3..5] hash lookup (which also keeps a 64 B/thread coupling queue in smem)
+constexpr size_t kSlicedCap[6] = {112640, 55296, 26624, 79872, 36864, 18432};
+constexpr size_t kSlicedMaxBlob = 16384;
 
 static int tile_cap_for(int nw32, int64_t K) {
     // keep a tile <= ~56 KB so four CTAs of 256 threads fit one SM; whole table in one tile when it fits
@@ -182,7 +183,7 @@ int naqs_table_create(naqs_table_t** out, const uint64_t* h_xy, const uint64_t* 
 
     // sliced (v2) stream: groups in ascending-XY order with their terms in reference order
     SlicedHost sh;
-    std::vector<STile> stiles[3];
+    std::vector<STile> stiles[6];
     {
         std::vector<HostGroup> hg((size_t)G);
         for (int64_t g = 0; g < G; ++g) {
@@ -195,7 +196,7 @@ int naqs_table_create(naqs_table_t** out, const uint64_t* h_xy, const uint64_t* 
                 for (int w = 0; w < NW; ++w) x.yz[(size_t)(i - b) * NW + w] = yz[(size_t)w * K + i];
         }
         build_sliced_host(hg, n_qubits, NW, kSlicedMaxBlob, sh);
-        for (int c = 0; c < 3; ++c) make_sliced_tiles(sh, kSlicedCap[c], stiles[c]);
+        for (int c = 0; c < 6; ++c) make_sliced_tiles(sh, kSlicedCap[c], stiles[c]);
         t->nn = sh.nn;
         t->stream_bytes = sh.stream.size();
     }
@@ -216,11 +217,14 @@ int naqs_table_create(naqs_table_t** out, const uint64_t* h_xy, const uint64_t* 
         (rc = upload((void**)&t->d_stream, sh.stream.data(), sh.stream.size())) ||
         (rc = upload(&t->d_stiles[0], stiles[0].data(), stiles[0].size() * sizeof(STile))) ||
         (rc = upload(&t->d_stiles[1], stiles[1].data(), stiles[1].size() * sizeof(STile))) ||
-        (rc = upload(&t->d_stiles[2], stiles[2].data(), stiles[2].size() * sizeof(STile)))) {
+        (rc = upload(&t->d_stiles[2], stiles[2].data(), stiles[2].size() * sizeof(STile))) ||
+        (rc = upload(&t->d_stiles[3], stiles[3].data(), stiles[3].size() * sizeof(STile))) ||
+        (rc = upload(&t->d_stiles[4], stiles[4].data(), stiles[4].size() * sizeof(STile))) ||
+        (rc = upload(&t->d_stiles[5], stiles[5].data(), stiles[5].size() * sizeof(STile)))) {
         naqs_table_destroy(t);
         return rc;
     }
-    for (int c = 0; c < 3; ++c) t->n_stiles[c] = (int)stiles[c].size();
+    for (int c = 0; c < 6; ++c) t->n_stiles[c] = (int)stiles[c].size();
     if (cudaStreamCreateWithFlags(&t->own_stream, cudaStreamNonBlocking) != cudaSuccess) t->own_stream = nullptr;
     *out = t;
     return NAQS_OK;
@@ -234,7 +238,7 @@ int naqs_table_destroy(naqs_table_t* t) {
     if (t->h_pinned) cudaFreeHost(t->h_pinned);
     if (t->own_stream) cudaStreamDestroy(t->own_stream);
     cudaFree(t->d_tiles); cudaFree(t->d_binom); cudaFree(t->d_stream); cudaFree(t->d_partial);
-    for (int c = 0; c < 3; ++c) cudaFree(t->d_stiles[c]);
+    for (int c = 0; c < 6; ++c) cudaFree(t->d_stiles[c]);
     delete t;
     return NAQS_OK;
 }
@@ -272,6 +276,7 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
     } else {
         int64_t cap = 1024;
         while (cap < 2 * n) cap <<= 1;
+        NAQS_REQUIRE(cap <= (1ll << 31), NAQS_ERR_ARG, "naqs_lookup_build: too many keys for the hash lookup (max 2^30)");
         if (t->hash_alloc < cap) {
             cudaFree(t->d_slots); t->d_slots = nullptr; t->hash_alloc = 0;
             NAQS_CUDA(cudaMalloc((void**)&t->d_slots, (size_t)cap * sizeof(HashSlot)));
@@ -281,7 +286,7 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
         hash_init_kernel<<<(int)((cap + 255) / 256), 256, 0, stream>>>(t->d_slots, cap);
         NAQS_LAUNCHED();
         if (n > 0) {
-            hash_insert_kernel<<<blocks, 256, 0, stream>>>(t->d_slots, (unsigned long long)(cap - 1), d_keys, t->words,
+            hash_insert_kernel<<<blocks, 256, 0, stream>>>(t->d_slots, (unsigned long long)(cap - 1), t->lookup().shift, d_keys, t->words,
                                                            d_psi, psi_dtype, n);
             NAQS_LAUNCHED();
         }
@@ -309,36 +314,53 @@ static int launch_eloc(naqs_table_t* t, const uint64_t* d_states, const void* d_
     return NAQS_OK;
 }
 
-template <int NW, int NN, int CFG, int LK, bool SEC>
-static int launch_sliced_cfg(naqs_table_t* t, const uint64_t* d_states, const void* d_psi, int psi_dtype, int64_t M,
+template <int NW, int NN, int CFG, int LK, bool SEC, bool KEYORDER>
+static int launch_sliced_cfg(naqs_table_t* t, const uint64_t* d_states, const void* d_psi, int psi_dtype, int64_t M_rows,
                              double* d_eloc, cudaStream_t stream, int n_chunks, int sm_count) {
+    // key-order mode walks all 2^N keys; otherwise one thread per row
+    const int64_t M = KEYORDER ? (1ll << t->n_qubits) : M_rows;
     constexpr int THREADS = kSlicedThreads[CFG];
-    const int n_tiles = t->n_stiles[CFG];
+    constexpr int TL = CFG + (LK == kLookHash ? 3 : 0);  // tile list of this launch shape
+    const int n_tiles = t->n_stiles[TL];
     const int tiles_per_chunk = std::max(1, (n_tiles + n_chunks - 1) / n_chunks);
     n_chunks = std::max(1, (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk);
-    const size_t cap = kSlicedCap[CFG];
+    const size_t cap = kSlicedCap[TL];
     const bool resident = tiles_per_chunk <= 1;
-    const size_t smem = resident ? cap : 2 * cap;
-    auto kern = eloc_sliced_kernel<NW, NN, THREADS, LK, SEC>;
-    NAQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * cap)));
+    const size_t queue_bytes = LK == kLookHash ? (size_t)kQueueCap * 4 * THREADS : 0;
+    const size_t queue_offset = resident ? cap : 2 * cap;
+    const size_t smem = queue_offset + queue_bytes;
+    auto kern = eloc_sliced_kernel<NW, NN, THREADS, LK, SEC, KEYORDER>;
+    NAQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * cap + queue_bytes)));
     double2* partial = nullptr;
-    if (n_chunks > 1) {
-        const size_t need = (size_t)n_chunks * M * sizeof(double2);
+    uint32_t* need_bits = nullptr;
+    if (n_chunks > 1 || KEYORDER) {
+        const size_t bitmap_bytes = KEYORDER ? (((size_t)M / 8 + 255) & ~(size_t)255) : 0;
+        const size_t need = (size_t)n_chunks * M * sizeof(double2) + bitmap_bytes;
         if (t->partial_bytes < need) {
             cudaFree(t->d_partial); t->d_partial = nullptr; t->partial_bytes = 0;
             NAQS_CUDA(cudaMalloc((void**)&t->d_partial, need));
             t->partial_bytes = need;
         }
         partial = t->d_partial;
+        if (KEYORDER) {
+            need_bits = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(t->d_partial) + (size_t)n_chunks * M * sizeof(double2));
+            NAQS_CUDA(cudaMemsetAsync(need_bits, 0, bitmap_bytes, stream));
+            mark_keys_kernel<<<(unsigned)((M_rows + 255) / 256), 256, 0, stream>>>(d_states, M_rows, need_bits);
+            NAQS_LAUNCHED();
+        }
     }
     const int64_t n_blocks = (M + THREADS - 1) / THREADS;
     const int slots = sm_count * (1024 / THREADS);
     dim3 grid((unsigned)std::min<int64_t>(n_blocks, slots), (unsigned)n_chunks);
-    SlicedView sv{t->d_stream, (const STile*)t->d_stiles[CFG], n_tiles, t->nn};
-    kern<<<grid, THREADS, smem, stream>>>(sv, tiles_per_chunk, (uint32_t)cap, t->sector, t->lookup(), d_states, d_psi, psi_dtype, M,
-                                          reinterpret_cast<double2*>(d_eloc), partial);
+    SlicedView sv{t->d_stream, (const STile*)t->d_stiles[TL], n_tiles, t->nn};
+    kern<<<grid, THREADS, smem, stream>>>(sv, tiles_per_chunk, (uint32_t)cap, (uint32_t)queue_offset, t->sector, t->lookup(), d_states, need_bits, d_psi, psi_dtype,
+                                          M, reinterpret_cast<double2*>(d_eloc), partial);
     NAQS_LAUNCHED();
-    if (n_chunks > 1) {
+    if (KEYORDER) {
+        eloc_rows_finalize_kernel<<<(unsigned)((M_rows + 255) / 256), 256, 0, stream>>>(partial, n_chunks, M, d_states, d_psi, psi_dtype,
+                                                                                      M_rows, reinterpret_cast<double2*>(d_eloc));
+        NAQS_LAUNCHED();
+    } else if (n_chunks > 1) {
         eloc_finalize_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(partial, n_chunks, d_psi, psi_dtype, M,
                                                                             reinterpret_cast<double2*>(d_eloc));
         NAQS_LAUNCHED();
@@ -351,6 +373,11 @@ static int launch_sliced(naqs_table_t* t, const uint64_t* d_states, const void* 
                          cudaStream_t stream) {
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, t->device);
+    // key-order mode: dense (direct-address) lookup and a batch that covers at least 1/8 of the key space
+    const bool keyorder = NW == 1 && t->lookup_kind == NAQS_LOOKUP_DENSE && t->n_qubits <= 26 && M >= (1ll << t->n_qubits) / 8 &&
+                          !getenv("NAQS_ELOC_NO_KEYORDER");
+    const int64_t M_rows = M;
+    if (keyorder) M = 1ll << t->n_qubits;  // launch shape is chosen for the number of threads that actually run
     // pick the launch shape: large CTAs when there are at least two waves of them, else smaller CTAs, and split the
     // table into chunks (grid.y) when even those cannot fill the machine
     int cfg = 2;
@@ -364,7 +391,7 @@ static int launch_sliced(naqs_table_t* t, const uint64_t* d_states, const void* 
         const int64_t slots = (int64_t)sm_count * (1024 / kSlicedThreads[cfg]);
         if (n_blocks < slots) {
             double best = -1.0;
-            const int max_chunks = std::min(t->n_stiles[cfg], 16);
+            const int max_chunks = std::min(t->n_stiles[cfg + (t->lookup_kind == NAQS_LOOKUP_HASH ? 3 : 0)], 16);
             for (int ch = 1; ch <= max_chunks; ++ch) {
                 const int64_t ctas = n_blocks * ch, waves = (ctas + slots - 1) / slots;
                 const double eff = (double)ctas / (double)(waves * slots) - 0.01 * ch;  // mild preference for fewer chunks
@@ -372,8 +399,23 @@ static int launch_sliced(naqs_table_t* t, const uint64_t* d_states, const void* 
             }
         }
     }
-#define NAQS_SL(CFG, LK, SEC) launch_sliced_cfg<NW, NN, CFG, LK, SEC>(t, d_states, d_psi, psi_dtype, M, d_eloc, stream, n_chunks, sm_count)
     const bool hash = t->lookup_kind == NAQS_LOOKUP_HASH, secf = t->sector.enabled != 0;
+    if constexpr (NW == 1) {
+        if (keyorder) {
+#define NAQS_KO(CFG, SEC) launch_sliced_cfg<NW, NN, CFG, kLookDense, SEC, true>(t, d_states, d_psi, psi_dtype, M_rows, d_eloc, stream, n_chunks, sm_count)
+            switch (cfg * 2 + (secf ? 1 : 0)) {
+                case 0: return NAQS_KO(0, false);
+                case 1: return NAQS_KO(0, true);
+                case 2: return NAQS_KO(1, false);
+                case 3: return NAQS_KO(1, true);
+                case 4: return NAQS_KO(2, false);
+                default: return NAQS_KO(2, true);
+            }
+#undef NAQS_KO
+        }
+    }
+    if (NW > 1 && !hash) { set_error("naqs_eloc: dense lookup needs n_qubits <= 30"); return NAQS_ERR_STATE; }
+#define NAQS_SL(CFG, LK, SEC) launch_sliced_cfg<NW, NN, CFG, (NW > 1 ? kLookHash : LK), SEC, false>(t, d_states, d_psi, psi_dtype, M, d_eloc, stream, n_chunks, sm_count)
     switch (cfg * 4 + (hash ? 2 : 0) + (secf ? 1 : 0)) {
         case 0: return NAQS_SL(0, kLookDense, false);
         case 1: return NAQS_SL(0, kLookDense, true);
