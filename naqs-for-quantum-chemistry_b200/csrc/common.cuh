@@ -88,12 +88,28 @@ struct alignas(32) HashSlot {
 static_assert(sizeof(HashSlot) == 32, "HashSlot must be one 32 B sector");
 constexpr unsigned long long kEmptyKey = ~0ull;
 
+// Bucketed hash for keys of <= 63 bits (all molecules): one probe = one 32-byte sector holding the 4 keys of a bucket.
+// A bucket that ever overflowed carries a flag in bit 63 of key[0]; without it a lookup ends after ONE sector read
+// whether it hits or misses (misses dominate a sparse VMC batch), so there is no dependent probe chain.
+struct alignas(128) HashBucket {
+    unsigned long long key[4];  // kEmptyKey63 when free; bit 63 of key[0] = "bucket overflowed into the next one"
+    double2 psi[4];
+    unsigned long long pad[4];
+};
+static_assert(sizeof(HashBucket) == 128, "HashBucket must be one 128 B line");
+constexpr unsigned long long kKeyMask63 = 0x7FFFFFFFFFFFFFFFull;
+constexpr unsigned long long kEmptyKey63 = kKeyMask63;
+constexpr unsigned long long kOverflowFlag = 0x8000000000000000ull;
+
 struct LookupView {
     const double2* dense;    // [2^N] (kind DENSE)
     const HashSlot* slots;   // [cap]  (kind HASH)
     unsigned long long mask; // cap - 1
     int kind;
     int shift;               // 32 - log2(cap): slot = hash32 >> shift
+    const HashBucket* buckets;  // [n_buckets] (kind HASH, keys <= 63 bits)
+    unsigned bmask;          // n_buckets - 1
+    int bshift;              // 32 - log2(n_buckets)
 };
 
 __host__ __device__ inline unsigned long long mix64(unsigned long long x) {
@@ -141,8 +157,10 @@ struct naqs_table {
     int64_t lookup_n = 0;
     double2* d_dense = nullptr;
     int64_t dense_entries = 0;
-    naqs::HashSlot* d_slots = nullptr;
+    naqs::HashSlot* d_slots = nullptr;     // 128-bit keys: 32 B slots, linear probing
     int64_t hash_cap = 0, hash_alloc = 0;
+    naqs::HashBucket* d_buckets = nullptr; // <= 63-bit keys: 128 B buckets of 4
+    int64_t n_buckets = 0, bucket_alloc = 0;
     // generic workspace (scan / sort temporaries, host-path staging)
     void* d_ws = nullptr;
     size_t ws_bytes = 0;
@@ -156,7 +174,10 @@ struct naqs_table {
     naqs::LookupView lookup() const {
         int shift = 32;
         for (int64_t c = hash_cap; c > 1; c >>= 1) --shift;
-        return naqs::LookupView{d_dense, d_slots, (unsigned long long)(hash_cap - 1), lookup_kind, shift};
+        int bshift = 32;
+        for (int64_t c = n_buckets; c > 1; c >>= 1) --bshift;
+        return naqs::LookupView{d_dense, d_slots, (unsigned long long)(hash_cap - 1), lookup_kind, shift,
+                                d_buckets, (unsigned)(n_buckets > 0 ? n_buckets - 1 : 0), bshift};
     }
 };
 

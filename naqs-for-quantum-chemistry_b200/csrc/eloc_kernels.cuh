@@ -53,6 +53,30 @@ __device__ __forceinline__ double2 load_psi(const void* __restrict__ psi, int dt
     return reinterpret_cast<const double2*>(psi)[m];
 }
 
+// the 4 keys of a bucket with ONE 256-bit load (sm_100a LDG.E.256): one request, one 32-byte sector
+struct BucketKeys {
+    unsigned long long k[4];
+};
+__device__ __forceinline__ BucketKeys load_bucket_keys(const HashBucket* __restrict__ bk) {
+    BucketKeys r;
+    asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(r.k[0]), "=l"(r.k[1]), "=l"(r.k[2]), "=l"(r.k[3]) : "l"(bk->key));
+    return r;
+}
+__device__ __forceinline__ int bucket_match(const BucketKeys& b, unsigned long long k0) {
+    int hs = -1;
+    if ((b.k[0] & kKeyMask63) == k0) hs = 0;
+    if (b.k[1] == k0) hs = 1;
+    if (b.k[2] == k0) hs = 2;
+    if (b.k[3] == k0) hs = 3;
+    return hs;
+}
+// one probe of the bucketed hash: -> true when the search is over (hit or definite miss)
+__device__ __forceinline__ bool bucket_probe(const HashBucket* __restrict__ bk, unsigned long long k0, int& hit_slot) {
+    const BucketKeys b = load_bucket_keys(bk);
+    hit_slot = bucket_match(b, k0);
+    return hit_slot >= 0 || !(b.k[0] & kOverflowFlag);
+}
+
 // psi(s') from the amplitude table; (0,0) when s' was not sampled.
 template <int NW>
 __device__ __forceinline__ double2 lookup_psi(const LookupView& lv, const uint32_t (&j)[NW]) {
@@ -61,13 +85,24 @@ __device__ __forceinline__ double2 lookup_psi(const LookupView& lv, const uint32
     if (lv.kind == NAQS_LOOKUP_DENSE) {
         return __ldg(lv.dense + k0);
     }
-    unsigned long long h = hash_slot(k0, k1, lv.shift);
-    while (true) {
-        const HashSlot* sl = lv.slots + h;
-        const ulonglong2 kk = __ldg(reinterpret_cast<const ulonglong2*>(sl));
-        if (kk.x == k0 && kk.y == k1) return __ldg(reinterpret_cast<const double2*>(sl) + 1);
-        if (kk.x == kEmptyKey && kk.y == kEmptyKey) return make_double2(0.0, 0.0);
-        h = (h + 1) & lv.mask;
+    if constexpr (NW <= 2) {
+        unsigned b = hash32(k0, 0ull) >> lv.bshift;
+        while (true) {
+            int hs;
+            const bool done = bucket_probe(lv.buckets + b, k0, hs);
+            if (hs >= 0) return __ldg(&lv.buckets[b].psi[hs]);
+            if (done) return make_double2(0.0, 0.0);
+            b = (b + 1) & lv.bmask;
+        }
+    } else {
+        unsigned long long h = hash_slot(k0, k1, lv.shift);
+        while (true) {
+            const HashSlot* sl = lv.slots + h;
+            const ulonglong2 kk = __ldg(reinterpret_cast<const ulonglong2*>(sl));
+            if (kk.x == k0 && kk.y == k1) return __ldg(reinterpret_cast<const double2*>(sl) + 1);
+            if (kk.x == kEmptyKey && kk.y == kEmptyKey) return make_double2(0.0, 0.0);
+            h = (h + 1) & lv.mask;
+        }
     }
 }
 

@@ -251,32 +251,68 @@ __device__ __forceinline__ void emit_batch(const double (&h)[B], const uint32_t*
     }
 }
 
-// Hash-lookup ("heavy") epilogue of one coupling: sector filter (hamiltonian.py:328), probe of the 32-byte-slot hash
-// table, complex multiply-add.  Called only for couplings whose H is not exactly 0.0 (hamiltonian.py:363), which the
-// per-thread queue of the kernel below makes dense across the warp.
-template <int NW, bool SEC>
-__device__ __forceinline__ void heavy_lookup(double h, const uint32_t* __restrict__ u, const uint32_t (&s)[NW], const Sector& sec,
-                                             const LookupView& lv, double& e_re, double& e_im) {
-    uint32_t j[NW];
+// Hash-lookup ("heavy") epilogue of up to B couplings of one thread: sector filter (hamiltonian.py:328), probe of the
+// 32-byte-slot hash table, complex multiply-add.  Called only for couplings whose H is not exactly 0.0
+// (hamiltonian.py:363), which the per-thread queue of the kernel below makes dense across the warp.  The first probes
+// of all B couplings are issued before any is examined, so their L2 latencies overlap.
+template <int NW, bool SEC, int B>
+__device__ __forceinline__ void heavy_lookup(int n, const double (&h)[B], const uint32_t* const (&u)[B], const uint32_t (&s)[NW],
+                                             const Sector& sec, const LookupView& lv, double& e_re, double& e_im) {
+    unsigned long long k0[B], k1[B];
+    unsigned slot[B];
+    bool on[B];
 #pragma unroll
-    for (int w = 0; w < NW; ++w) j[w] = s[w] ^ u[w];
-    if constexpr (SEC) {
-        if (!in_sector<NW>(j, sec)) return;
+    for (int b = 0; b < B; ++b) {
+        on[b] = b < n;
+        uint32_t j[NW];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) j[w] = on[b] ? (s[w] ^ u[b][w]) : s[w];
+        if constexpr (SEC) on[b] = on[b] && in_sector<NW>(j, sec);
+        key_words64<NW>(j, k0[b], k1[b]);
+        slot[b] = NW <= 2 ? (hash32(k0[b], 0ull) >> lv.bshift) : (unsigned)hash_slot(k0[b], k1[b], lv.shift);
     }
-    unsigned long long k0, k1;
-    key_words64<NW>(j, k0, k1);
-    unsigned long long slot = hash_slot(k0, k1, lv.shift);
-    while (true) {  // linear probing; load factor <= 0.5, the first probe almost always decides
-        const HashSlot* sl = lv.slots + slot;
-        const ulonglong2 kk = __ldg(reinterpret_cast<const ulonglong2*>(sl));
-        if (kk.x == k0 && kk.y == k1) {
-            const double2 p = __ldg(reinterpret_cast<const double2*>(sl) + 1);
-            e_re = __fma_rn(h, p.x, e_re);
-            e_im = __fma_rn(h, p.y, e_im);
-            return;
+    if constexpr (NW <= 2) {
+        // bucketed table: the 4 keys of a bucket are one sector; all B first probes are in flight together
+        BucketKeys bk[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) bk[b] = load_bucket_keys(lv.buckets + (on[b] ? slot[b] : 0u));
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            if (on[b]) {
+                while (true) {
+                    const int hs = bucket_match(bk[b], k0[b]);
+                    if (hs >= 0) {
+                        const double2 p = __ldg(&lv.buckets[slot[b]].psi[hs]);
+                        e_re = __fma_rn(h[b], p.x, e_re);
+                        e_im = __fma_rn(h[b], p.y, e_im);
+                        break;
+                    }
+                    if (!(bk[b].k[0] & kOverflowFlag)) break;  // bucket never overflowed: definite miss after one sector
+                    slot[b] = (slot[b] + 1) & lv.bmask;
+                    bk[b] = load_bucket_keys(lv.buckets + slot[b]);
+                }
+            }
         }
-        if (kk.x == kEmptyKey && kk.y == kEmptyKey) return;
-        slot = (slot + 1) & lv.mask;
+    } else {
+        ulonglong2 kk[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) kk[b] = __ldg(reinterpret_cast<const ulonglong2*>(lv.slots + (on[b] ? slot[b] : 0u)));
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            if (on[b]) {
+                while (true) {  // 128-bit keys: 32 B slots, linear probing
+                    if (kk[b].x == k0[b] && kk[b].y == k1[b]) {
+                        const double2 p = __ldg(reinterpret_cast<const double2*>(lv.slots + slot[b]) + 1);
+                        e_re = __fma_rn(h[b], p.x, e_re);
+                        e_im = __fma_rn(h[b], p.y, e_im);
+                        break;
+                    }
+                    if (kk[b].x == kEmptyKey && kk[b].y == kEmptyKey) break;
+                    slot[b] = (slot[b] + 1) & (unsigned)lv.mask;
+                    kk[b] = __ldg(reinterpret_cast<const ulonglong2*>(lv.slots + slot[b]));
+                }
+            }
+        }
     }
 }
 
@@ -345,19 +381,27 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
         // fraction of the (state, group) pairs couples.  The queue is drained before a tile buffer is released.
         uint32_t qcnt = 0;
         uint32_t* const q = reinterpret_cast<uint32_t*>(smem + queue_offset) + threadIdx.x;
+        constexpr int PB = 4;  // couplings resolved per thread and round
         auto pop_round = [&](const unsigned char* __restrict__ buf) {
-            if (qcnt > 0) {
-                --qcnt;
-                const uint32_t e = q[qcnt * THREADS];
-                heavy_lookup<NW, SEC>(*reinterpret_cast<const double*>(buf + (e & 0xffffu) * 8u),
-                                      reinterpret_cast<const uint32_t*>(buf + (e >> 16) * 4u), s, sec, lv, e_re, e_im);
+            const int n = min((int)qcnt, PB);
+            double h[PB];
+            const uint32_t* u[PB];
+#pragma unroll
+            for (int b = 0; b < PB; ++b) {
+                h[b] = 0.0; u[b] = reinterpret_cast<const uint32_t*>(buf);
+                if (b < n) {
+                    const uint32_t e = q[(qcnt - 1 - b) * THREADS];
+                    h[b] = *reinterpret_cast<const double*>(buf + (e & 0xffffu) * 8u);
+                    u[b] = reinterpret_cast<const uint32_t*>(buf + (e >> 16) * 4u);
+                }
             }
+            qcnt -= n;
+            heavy_lookup<NW, SEC, PB>(n, h, u, s, sec, lv, e_re, e_im);
         };
-        auto push = [&](double h, const unsigned char* __restrict__ buf, const unsigned char* lut_entry, const uint32_t* u) {
-            if (h != 0.0 && valid) {
-                q[qcnt * THREADS] = (uint32_t)((lut_entry - buf) >> 3) | ((uint32_t)((reinterpret_cast<const unsigned char*>(u) - buf) >> 2) << 16);
-                ++qcnt;
-            }
+        // branch-free: the entry is always written at the tail, the tail only advances for a live coupling
+        auto push = [&](double h, uint32_t lut_off8, uint32_t u_off4) {
+            q[qcnt * THREADS] = lut_off8 | (u_off4 << 16);
+            qcnt += (h != 0.0 && valid) ? 1u : 0u;
         };
 
         auto process = [&](const unsigned char* __restrict__ buf, const STile& tl) {
@@ -381,10 +425,11 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                         }
                     } else {
 #pragma unroll
+                        const uint32_t l8 = (uint32_t)(L - buf) >> 3, u4 = (uint32_t)(reinterpret_cast<const unsigned char*>(U) - buf) >> 2;
+#pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const uint32_t off = j == 0 ? ((P << 3) & 0x78u) : ((P >> (4 * j - 3)) & 0x78u);
-                            const unsigned char* le = L + j * 128 + off;
-                            push(*reinterpret_cast<const double*>(le), buf, le, U + j * NW);
+                            push(*reinterpret_cast<const double*>(L + j * 128 + off), l8 + j * 16 + (off >> 3), u4 + j * NW);
                         }
                         while (__any_sync(0xffffffffu, qcnt > kQueueCap - 8)) pop_round(buf);
                     }
@@ -405,10 +450,11 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                         emit_batch<NW, SEC, KEYORDER, 5>(h, U, NW, s, valid, sec, lv, e_re, e_im);
                     } else {
 #pragma unroll
+                        const uint32_t l8 = (uint32_t)(L - buf) >> 3, u4 = (uint32_t)(reinterpret_cast<const unsigned char*>(U) - buf) >> 2;
+#pragma unroll
                         for (int j = 0; j < 5; ++j) {
                             const uint32_t off = j == 0 ? ((P << 3) & 0x1f8u) : ((P >> (6 * j - 3)) & 0x1f8u);
-                            const unsigned char* le = L + j * 512 + off;
-                            push(*reinterpret_cast<const double*>(le), buf, le, U + j * NW);
+                            push(*reinterpret_cast<const double*>(L + j * 512 + off), l8 + j * 64 + (off >> 3), u4 + j * NW);
                         }
                         while (__any_sync(0xffffffffu, qcnt > kQueueCap - 8)) pop_round(buf);
                     }
@@ -442,7 +488,10 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                     if (flags & kBlobLast) {
                         double h[1] = {__hiloint2double(__double2hiint(acc) ^ (int)flip, __double2loint(acc))};
                         if constexpr (LK == kLookDense) emit_batch<NW, SEC, KEYORDER, 1>(h, hdr + 4, NW, s, valid, sec, lv, e_re, e_im);
-                        else if (h[0] != 0.0 && valid) heavy_lookup<NW, SEC>(h[0], hdr + 4, s, sec, lv, e_re, e_im);
+                        else {
+                            const uint32_t* uu[1] = {hdr + 4};
+                            heavy_lookup<NW, SEC, 1>((h[0] != 0.0 && valid) ? 1 : 0, h, uu, s, sec, lv, e_re, e_im);
+                        }
                     }
                     p += kBlobHeader + (size_t)n_words * REC_C;
                 }

@@ -66,6 +66,36 @@ __global__ void hash_insert_kernel(HashSlot* slots, unsigned long long mask, int
     }
 }
 
+__global__ void bucket_init_kernel(HashBucket* buckets, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 32 B quarter of a bucket
+    if (i >= 4 * n) return;
+    ulonglong4 v = (i & 3) == 0 ? make_ulonglong4(kEmptyKey63, kEmptyKey63, kEmptyKey63, kEmptyKey63) : make_ulonglong4(0, 0, 0, 0);
+    reinterpret_cast<ulonglong4*>(buckets)[i] = v;
+}
+
+__global__ void bucket_insert_kernel(HashBucket* buckets, unsigned bmask, int bshift, const uint64_t* __restrict__ keys, int words,
+                                     const void* __restrict__ psi, int psi_dtype, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = keys[i * words];
+    const double2 p = load_psi(psi, psi_dtype, i);
+    unsigned b = hash32(k, 0ull) >> bshift;
+    while (true) {
+        HashBucket* bk = buckets + b;
+        for (int s = 0; s < 4; ++s) {
+            const unsigned long long old = atomicCAS(&bk->key[s], kEmptyKey63, k);
+            if (old == kEmptyKey63 || (old & kKeyMask63) == k) {
+                // duplicates of a key are summed (scipy's H[idx[:,None], idx] repeats the column)
+                atomicAdd(&bk->psi[s].x, p.x);
+                atomicAdd(&bk->psi[s].y, p.y);
+                return;
+            }
+        }
+        atomicOr(&bk->key[0], kOverflowFlag);  // full: later searches must continue with the next bucket
+        b = (b + 1) & bmask;
+    }
+}
+
 __global__ void dense_scatter_kernel(double2* dense, const uint64_t* __restrict__ keys, const void* __restrict__ psi,
                                      int psi_dtype, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -234,7 +264,7 @@ int naqs_table_destroy(naqs_table_t* t) {
     if (!t) return NAQS_OK;
     DeviceGuard guard(t->device);
     cudaFree(t->d_yz); cudaFree(t->d_coeff); cudaFree(t->d_gxy); cudaFree(t->d_gstart);
-    cudaFree(t->d_dense); cudaFree(t->d_slots); cudaFree(t->d_ws); cudaFree(t->d_stage);
+    cudaFree(t->d_dense); cudaFree(t->d_slots); cudaFree(t->d_buckets); cudaFree(t->d_ws); cudaFree(t->d_stage);
     if (t->h_pinned) cudaFreeHost(t->h_pinned);
     if (t->own_stream) cudaStreamDestroy(t->own_stream);
     cudaFree(t->d_tiles); cudaFree(t->d_binom); cudaFree(t->d_stream); cudaFree(t->d_partial);
@@ -273,9 +303,30 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
             dense_scatter_kernel<<<blocks, 256, 0, stream>>>(t->d_dense, d_keys, d_psi, psi_dtype, n);
             NAQS_LAUNCHED();
         }
+    } else if (t->nw32 <= 2) {
+        // bucketed table: 4 slots per 128 B bucket; load factor <= 0.25 while it stays well inside L2, else <= 0.5
+        int64_t nb = 256;
+        while (4 * nb < 4 * n) nb <<= 1;
+        if (nb * (int64_t)sizeof(HashBucket) > (64ll << 20) && 4 * nb >= 4 * n) nb >>= 1;
+        NAQS_REQUIRE(nb <= (1ll << 30), NAQS_ERR_ARG, "naqs_lookup_build: too many keys for the hash lookup");
+        if (t->bucket_alloc < nb) {
+            cudaFree(t->d_buckets); t->d_buckets = nullptr; t->bucket_alloc = 0;
+            NAQS_CUDA(cudaMalloc((void**)&t->d_buckets, (size_t)nb * sizeof(HashBucket)));
+            t->bucket_alloc = nb;
+        }
+        t->n_buckets = nb;
+        bucket_init_kernel<<<(unsigned)((4 * nb + 255) / 256), 256, 0, stream>>>(t->d_buckets, nb);
+        NAQS_LAUNCHED();
+        if (n > 0) {
+            const LookupView lv = t->lookup();
+            bucket_insert_kernel<<<blocks, 256, 0, stream>>>(t->d_buckets, lv.bmask, lv.bshift, d_keys, t->words, d_psi, psi_dtype, n);
+            NAQS_LAUNCHED();
+        }
     } else {
+        // load factor <= 0.25 while the table stays well inside L2 (32 B slots), else <= 0.5
         int64_t cap = 1024;
-        while (cap < 2 * n) cap <<= 1;
+        while (cap < 4 * n) cap <<= 1;
+        if (cap * (int64_t)sizeof(HashSlot) > (48ll << 20) && cap >= 4 * n) cap >>= 1;
         NAQS_REQUIRE(cap <= (1ll << 31), NAQS_ERR_ARG, "naqs_lookup_build: too many keys for the hash lookup (max 2^30)");
         if (t->hash_alloc < cap) {
             cudaFree(t->d_slots); t->d_slots = nullptr; t->hash_alloc = 0;
@@ -380,24 +431,24 @@ static int launch_sliced(naqs_table_t* t, const uint64_t* d_states, const void* 
     if (keyorder) M = 1ll << t->n_qubits;  // launch shape is chosen for the number of threads that actually run
     // pick the launch shape: large CTAs when there are at least two waves of them, else smaller CTAs, and split the
     // table into chunks (grid.y) when even those cannot fill the machine
-    int cfg = 2;
+    // launch shape: the largest CTA (fewest tile switches, least table re-streaming) whose grid — state blocks x table
+    // chunks (grid.y) — fills the machine to >= 85 %; otherwise the best fill found
+    const int tl_off = t->lookup_kind == NAQS_LOOKUP_HASH ? 3 : 0;
+    int cfg = 2, n_chunks = 1;
+    double best_eff = -1.0;
     for (int c = 0; c < 3; ++c) {
         const int64_t n_blocks = (M + kSlicedThreads[c] - 1) / kSlicedThreads[c];
-        if (n_blocks >= 2ll * sm_count * (1024 / kSlicedThreads[c])) { cfg = c; break; }
-    }
-    int n_chunks = 1;
-    {
-        const int64_t n_blocks = (M + kSlicedThreads[cfg] - 1) / kSlicedThreads[cfg];
-        const int64_t slots = (int64_t)sm_count * (1024 / kSlicedThreads[cfg]);
-        if (n_blocks < slots) {
-            double best = -1.0;
-            const int max_chunks = std::min(t->n_stiles[cfg + (t->lookup_kind == NAQS_LOOKUP_HASH ? 3 : 0)], 16);
-            for (int ch = 1; ch <= max_chunks; ++ch) {
-                const int64_t ctas = n_blocks * ch, waves = (ctas + slots - 1) / slots;
-                const double eff = (double)ctas / (double)(waves * slots) - 0.01 * ch;  // mild preference for fewer chunks
-                if (eff > best) { best = eff; n_chunks = ch; }
-            }
+        const int64_t slots = (int64_t)sm_count * (1024 / kSlicedThreads[c]);
+        const int max_chunks = n_blocks >= slots ? 1 : std::min(t->n_stiles[c + tl_off], 16);
+        int ch_best = 1;
+        double eff_best = -1.0;
+        for (int ch = 1; ch <= max_chunks; ++ch) {
+            const int64_t ctas = n_blocks * ch, waves = (ctas + slots - 1) / slots;
+            const double eff = n_blocks >= slots ? 1.0 : (double)ctas / (double)(waves * slots) - 0.005 * ch;
+            if (eff > eff_best) { eff_best = eff; ch_best = ch; }
         }
+        if (eff_best > best_eff + 1e-9) { best_eff = eff_best; cfg = c; n_chunks = ch_best; }
+        if (eff_best >= 0.85) { cfg = c; n_chunks = ch_best; break; }
     }
     const bool hash = t->lookup_kind == NAQS_LOOKUP_HASH, secf = t->sector.enabled != 0;
     if constexpr (NW == 1) {
