@@ -290,9 +290,9 @@ def main():
     def step(states, psi, out):
         """One pass of the hot path with device-resident inputs; returns the 5 statistics sums (device)."""
         if world > 1:
-            dist.all_gather_into_tensor(g_states, states)
-            dist.all_gather_into_tensor(g_psi, psi)
-            table.build_lookup(g_states, g_psi)
+            # public multi-GPU API: all-gather (key, psi) -> lookup build -> fused E_loc on the shard -> all-reduce of 5 sums
+            g_k, g_p, _ = naqs_b200.distributed.gather_table(states, psi, equal_sizes=True, out=(g_states, g_psi))
+            table.build_lookup(g_k, g_p)
         elif dedup:
             table.build_lookup(t_keys, t_psi)
         else:
@@ -300,10 +300,7 @@ def main():
         ev_k0.record()
         table.local_energy(states, psi, out=out, rebuild_lookup=False)
         ev_k1.record()
-        s5 = table.stats(out)
-        if world > 1:
-            dist.all_reduce(s5)
-        return s5
+        return naqs_b200.distributed.reduce_stats(table.stats(out))
 
     ev_k0, ev_k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -344,12 +341,14 @@ def main():
     if not args.no_e2e:
         def e2e_step():
             if world == 1 and not dedup:
-                return table.local_energy_host(h_states.numpy().view(np.uint64), h_psi.numpy())
+                return table.local_energy_host(h_states_np, h_psi_np, out=h_eloc_np)
             ds, dp = h_states.to(dev, non_blocking=True), h_psi.to(dev, non_blocking=True)
             step(ds, dp, d_eloc)
             h_eloc.copy_(d_eloc, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return h_eloc
+        h_states_np, h_psi_np = h_states.numpy().view(np.uint64), h_psi.numpy()       # views of the pinned buffers
+        h_eloc_np = torch.view_as_complex(h_eloc).numpy()
         for _ in range(3):
             e2e_step()
         barrier()

@@ -8,6 +8,7 @@ No CPU fallback: compute entries raise without the CUDA library / a CUDA device.
 """
 from . import _lib  # noqa: F401
 from ._lib import NaqsError, launch_count  # noqa: F401
+from . import distributed  # noqa: F401
 from .energy import calculate_local_energy, local_energy_statistics, stats_from_sums  # noqa: F401
 from .hamiltonian import PauliHamiltonian, PauliHamiltonianB200  # noqa: F401
 from .hilbert import Encoding, Hilbert  # noqa: F401

@@ -1,0 +1,101 @@
+"""Multi-GPU local energy: one process per GPU, the unique-state batch sharded across ranks.
+
+The reference has no distributed code at all (single process); this module adds the only exchange steps the
+path needs, with torch.distributed as plumbing (NCCL over NVLink on GPUs, gloo in the CPU tests):
+
+  1. all-gather of the per-rank (key, psi) shards  -> every rank holds the full amplitude lookup table
+  2. fused E_loc kernel on the local shard (rows are independent given the table; the Pauli table is replicated)
+  3. all-reduce (sum) of five fp64 scalars [sum w, sum w Re E, sum w Im E, sum w (Re E)^2, n]
+     (the quantities of src/optimizer/energy.py:328,372-375)
+
+E_loc itself stays sharded: the loss only needs the global mean.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .energy import stats_from_sums
+
+
+def shard_bounds(n, world_size, rank):
+    """Contiguous block partition of n rows: rank r owns [lo, hi); the first n % world_size ranks get one extra row."""
+    base, extra = divmod(int(n), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _world(group):
+    if not dist.is_available() or not dist.is_initialized():
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def gather_table(keys, psi, group=None, equal_sizes=False, out=None):
+    """All-gather the (key, psi) shards of every rank -> (keys [T, W] int64 bit patterns, psi [T] complex).
+
+    equal_sizes=True skips the size exchange (and its host synchronisation) when every rank is known to hold the same
+    number of rows; out=(g_keys, g_psi) reuses preallocated gather buffers.
+
+    Shards may have different lengths: each is padded to the longest with (its own first key or 0, psi = 0); a padded
+    entry adds exactly 0 to the amplitude of a key (duplicates are summed by the lookup build), so no un-padding pass
+    is needed on the device.  Returns the padded gathered arrays and the true total count."""
+    world, rank = _world(group)
+    keys = keys if keys.dim() == 2 else keys.reshape(-1, 1)
+    if world == 1:
+        return keys, psi, keys.shape[0]
+    if equal_sizes:
+        counts = [keys.shape[0]] * world
+    else:
+        n = torch.tensor([keys.shape[0]], dtype=torch.int64, device=keys.device)
+        counts = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(counts, n, group=group)
+        counts = [int(c.item()) for c in counts]
+    n_max = max(counts)
+    if keys.shape[0] < n_max:
+        pad = n_max - keys.shape[0]
+        fill = keys[:1] if keys.shape[0] > 0 else torch.zeros((1, keys.shape[1]), dtype=keys.dtype, device=keys.device)
+        keys = torch.cat([keys, fill.expand(pad, -1)], 0)
+        psi = torch.cat([psi, torch.zeros(pad, dtype=psi.dtype, device=psi.device)], 0)
+    if out is not None:
+        g_keys, g_psi = out
+    else:
+        g_keys = torch.empty((world * n_max, keys.shape[1]), dtype=keys.dtype, device=keys.device)
+        g_psi = torch.empty(world * n_max, dtype=psi.dtype, device=psi.device)
+    if keys.is_cuda:
+        dist.all_gather_into_tensor(g_keys, keys.contiguous(), group=group)
+        dist.all_gather_into_tensor(torch.view_as_real(g_psi), torch.view_as_real(psi.contiguous()), group=group)
+    else:  # gloo: list form
+        dist.all_gather(list(g_keys.chunk(world, 0)), keys.contiguous(), group=group)
+        dist.all_gather(list(torch.view_as_real(g_psi).chunk(world, 0)), torch.view_as_real(psi.contiguous()), group=group)
+    return g_keys, g_psi, sum(counts)
+
+
+def reduce_stats(sums5, group=None):
+    """All-reduce (sum) the five statistics sums; returns the reduced tensor (in place)."""
+    world, _ = _world(group)
+    if world > 1:
+        dist.all_reduce(sums5, op=dist.ReduceOp.SUM, group=group)
+    return sums5
+
+
+def sharded_local_energy(table, keys_shard, psi_shard, weights_shard=None, group=None, out=None, equal_sizes=False, gather_out=None):
+    """E_loc of this rank's shard against the batch of ALL ranks, plus the globally reduced statistics.
+
+    table: DeviceTermTable (replicated on every rank); keys_shard / psi_shard: CUDA tensors (or host arrays) of the
+    local unique states and their amplitudes.  -> (eloc_shard float64 [m, 2] on the device, the five reduced sums as a
+    device tensor; `stats_from_sums` turns them into mean / variance)."""
+    from . import _lib
+    k = _lib.keys_to_device(keys_shard, table.words, table.device)
+    p, _ = _lib.psi_to_device(psi_shard, table.device)
+    pc = torch.view_as_complex(p)
+    g_keys, g_psi, _ = gather_table(k, pc, group, equal_sizes=equal_sizes, out=gather_out)
+    table.build_lookup(g_keys, g_psi)
+    eloc = table.local_energy(k, pc, out=out, rebuild_lookup=False)
+    sums = reduce_stats(table.stats(eloc, weights_shard), group)
+    return eloc, sums
+
+
+def sharded_local_energy_stats(table, keys_shard, psi_shard, weights_shard=None, group=None):
+    """Convenience wrapper: -> (eloc_shard, dict(sum_w, mean, variance, n)) with the statistics brought to the host."""
+    eloc, sums = sharded_local_energy(table, keys_shard, psi_shard, weights_shard, group)
+    return eloc, stats_from_sums(sums.cpu().numpy())

@@ -98,15 +98,19 @@ class DeviceTermTable:
             _lib.check(_lib.load().naqs_eloc(self._h, _lib.ptr(k), _lib.ptr(p), code, M, _lib.ptr(out), self._stream()), "naqs_eloc")
         return out
 
-    def local_energy_host(self, states, psi, table_keys=None, table_psi=None):
-        """Host-buffer path (numpy in, numpy complex128 out) through naqs_eloc_host: pinned-free
-        synchronous upload -> lookup build -> fused kernel -> download."""
+    def local_energy_host(self, states, psi, table_keys=None, table_psi=None, out=None):
+        """Host-buffer path (numpy in, numpy complex128 out) through naqs_eloc_host: upload -> lookup build -> fused
+        kernel -> download, synchronous.  Page-locked inputs / `out` (e.g. numpy views of pinned torch tensors) make the
+        copies run at full PCIe rate; pageable arrays work too, only slower."""
         k = _lib.keys_to_numpy(states, self.words)
         p = np.ascontiguousarray(psi)
         if p.dtype not in (np.complex64, np.complex128):
             p = p.astype(np.complex128)
         code = _lib.NAQS_C64 if p.dtype == np.complex64 else _lib.NAQS_C128
-        out = np.empty(len(k), np.complex128)
+        if out is None:
+            out = np.empty(len(k), np.complex128)
+        elif out.dtype != np.complex128 or out.shape != (len(k),) or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous complex128 array with one entry per state")
         tk = tp = None
         T = 0
         if table_keys is not None:

@@ -156,3 +156,37 @@ def test_type_mv_promotion_rules():
         assert nb == bits and vv.dtype == out_dt and mm.dtype == (np.float64 if bits == 64 else np.float32)
     with pytest.raises(Exception):
         sparse_math._type_mv(identity(3, dtype=np.int32, format="csr"), np.ones(3))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/optimizer"), reason="reference tree not present (GPU box)")
+def test_install_patches_the_unmodified_reference():
+    """install() makes the reference's own import statements resolve to the device-backed twins and rebinds the two
+    Level-1 seams; run in a subprocess so the patched modules do not leak into the other tests."""
+    import subprocess
+    import sys
+    code = r'''
+import sys
+sys.path.insert(0, "%s")
+from oracle import ref_harness
+ref_harness.install_stubs()            # openfermion / torch._six stand-ins the reference needs to import at all
+import naqs_b200
+assert naqs_b200.install("/root/reference")
+import src.utils.hamiltonian_math as hm, src.utils.sparse_math as sm, src.utils.hilbert_math as him
+assert hm is naqs_b200.hamiltonian_math and sm is naqs_b200.sparse_math and him is naqs_b200.hilbert_math
+import src.optimizer.hamiltonian as H, src.optimizer.energy as E
+assert H.get_Hij_cy is naqs_b200.hamiltonian_math.get_Hij_cy          # hamiltonian.py:13 picked up the twin
+assert E.sparse_dense_mv is naqs_b200.sparse_math.sparse_dense_mv    # energy.py:27
+assert E.OptimizerBase.calculate_local_energy is naqs_b200.calculate_local_energy
+assert H.PauliHamiltonian.get is naqs_b200.PauliHamiltonian.get
+import inspect
+ref_sig = ["self", "states_idx", "psi", "set_unsampled_states_to_zero", "ret_complex"]
+assert list(inspect.signature(naqs_b200.calculate_local_energy).parameters) == ref_sig
+print("ok")
+''' % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_reference_backend_switch_leaves_reference_alone(monkeypatch):
+    monkeypatch.setenv("NAQS_ELOC_BACKEND", "reference")
+    assert naqs_b200.install("/nonexistent") is False

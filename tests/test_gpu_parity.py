@@ -421,3 +421,53 @@ def test_full_size_li2o_1e5():
     ref = ct.local_energy(st[sub], psi[sub], st, psi)
     assert rel_err(e[sub], ref).max() <= ELOC_RTOL
     assert np.array_equal(gpu_eloc(t, st, psi * np.complex64(0.5)), e)
+
+
+# ------------------------------------------------------------------------------------------- multi-GPU (needs >= 2 GPUs)
+def _mgpu_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import naqs_b200
+        from naqs_b200 import distributed as nd
+        xy, yz, c, N, na, nb = load_table("N2")
+        t = naqs_b200.DeviceTermTable(xy, yz, c, N, na, nb, device=f"cuda:{rank}")
+        st = random_sector_states(N, na, nb, 5001, seed=77)  # odd size: uneven shards
+        rng = np.random.default_rng(78)
+        psi = (rng.normal(size=len(st)) + 1j * rng.normal(size=len(st))).astype(np.complex64)
+        lo, hi = nd.shard_bounds(len(st), world, rank)
+        eloc, stats = nd.sharded_local_energy_stats(t, st[lo:hi], psi[lo:hi])
+        q.put((rank, lo, hi, naqs_b200._lib.complex_from_pairs(eloc), stats))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_local_energy_two_gpus():
+    import socket
+    import torch.multiprocessing as mp
+    nb200, c_oracle, eo = _mods()
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_mgpu_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=300) for _ in range(2)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    xy, yz, c, N, na, nb = load_table("N2")
+    st = random_sector_states(N, na, nb, 5001, seed=77)
+    rng = np.random.default_rng(78)
+    psi = (rng.normal(size=len(st)) + 1j * rng.normal(size=len(st))).astype(np.complex64)
+    ref = c_oracle.COracleTable(xy, yz, c, N, na, nb).local_energy(st, psi)
+    got = np.concatenate([r[3] for r in res])
+    assert res[0][1] == 0 and res[0][2] == res[1][1] and res[1][2] == len(st)
+    assert rel_err(got, ref).max() <= ELOC_RTOL
+    for r in res:  # every rank holds the same globally reduced statistics
+        assert r[4]["n"] == len(st) and abs(r[4]["mean"] - ref.mean()) <= 1e-12 * abs(ref.mean())
