@@ -93,6 +93,12 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
 int naqs_eloc(naqs_table_t* t, const uint64_t* d_states, const void* d_psi, int psi_dtype, int64_t n_states,
               double* d_eloc, void* stream);
 
+/* Matrix-free H.v — the same kernels without the division: out[m] = sum_u H[s_m, s_m^u] * v(s_m^u), complex128, where
+ * the vector v is what the last naqs_lookup_build stored (keys = basis states, "psi" = v).  This is the mat-vec that
+ * OptimizerBase.solve_H / calculate_energy obtain from the cached scipy CSR (src/optimizer/energy.py:199-217,762-786)
+ * — here no matrix is ever formed. */
+int naqs_apply_h(naqs_table_t* t, const uint64_t* d_states, int64_t n_states, double* d_out, void* stream);
+
 /* Kernel formulation used by naqs_eloc: 0 = nibble-sliced parity + group LUT (default), 1 = direct
  * AND/POPC walk (the formulation of hamiltonian_math.pyx:449-451, 31-34 transcribed; kept for A/B checks).
  * Both give bit-identical H_ij.  The environment variable NAQS_ELOC_ALGO=direct sets the default. */

@@ -110,7 +110,18 @@ struct LookupView {
     const HashBucket* buckets;  // [n_buckets] (kind HASH, keys <= 63 bits)
     unsigned bmask;          // n_buckets - 1
     int bshift;              // 32 - log2(n_buckets)
+    const uint32_t* filter;  // Bloom filter over the table keys (kFilterBits bits, 2 probes) or nullptr
 };
+
+// Bloom filter of the hash lookup: 2^19 bits = 64 KB, copied into shared memory by every CTA of the 1024-thread launch
+// shape.  In a sparse VMC batch almost every coupled state is NOT in the table; the filter answers those with two
+// shared-memory reads instead of a global sector read.  Built only while it has >= 4 bits per key.
+constexpr uint32_t kFilterBits = 1u << 19;
+constexpr uint32_t kFilterBytes = kFilterBits / 8;
+__host__ __device__ inline void filter_positions(uint32_t h, uint32_t& b1, uint32_t& b2) {
+    b1 = h & (kFilterBits - 1);
+    b2 = (h * 0x9E3779B1u) >> (32 - 19);
+}
 
 __host__ __device__ inline unsigned long long mix64(unsigned long long x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
@@ -161,6 +172,8 @@ struct naqs_table {
     int64_t hash_cap = 0, hash_alloc = 0;
     naqs::HashBucket* d_buckets = nullptr; // <= 63-bit keys: 128 B buckets of 4
     int64_t n_buckets = 0, bucket_alloc = 0;
+    uint32_t* d_filter = nullptr;          // Bloom filter storage (kFilterBytes)
+    bool filter_valid = false;
     // generic workspace (scan / sort temporaries, host-path staging)
     void* d_ws = nullptr;
     size_t ws_bytes = 0;
@@ -177,7 +190,8 @@ struct naqs_table {
         int bshift = 32;
         for (int64_t c = n_buckets; c > 1; c >>= 1) --bshift;
         return naqs::LookupView{d_dense, d_slots, (unsigned long long)(hash_cap - 1), lookup_kind, shift,
-                                d_buckets, (unsigned)(n_buckets > 0 ? n_buckets - 1 : 0), bshift};
+                                d_buckets, (unsigned)(n_buckets > 0 ? n_buckets - 1 : 0), bshift,
+                                filter_valid ? d_filter : nullptr};
     }
 };
 

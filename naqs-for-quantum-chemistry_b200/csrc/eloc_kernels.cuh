@@ -129,6 +129,12 @@ __device__ __forceinline__ double2 div_conj(double2 a, double2 b) {
     return make_double2(qr, -qi);
 }
 
+// finalisation of one row: E_loc = conj(S / psi) (energy.py:248), or the raw sum S = (H psi)[row] when psi == nullptr
+// (matrix-free H.v for solve_H / calculate_energy)
+__device__ __forceinline__ double2 finalize_row(double2 sum, const void* __restrict__ psi, int psi_dtype, int64_t m) {
+    return psi ? div_conj(sum, load_psi(psi, psi_dtype, m)) : sum;
+}
+
 // +c or -c according to the parity of popcount(f): the sign bit goes straight into the high word.
 __device__ __forceinline__ double signed_coeff(int c_hi, int c_lo, uint32_t f) {
     return __hiloint2double(c_hi ^ (int)(__popc(f) << 31), c_lo);
@@ -256,7 +262,7 @@ eloc_direct_kernel(TableView tv, const Tile* __restrict__ tiles, int n_tiles, in
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int64_t m = base + (int64_t)r * THREADS;
-        if (valid[r]) out[m] = div_conj(make_double2(e_re[r], e_im[r]), load_psi(psi, psi_dtype, m));
+        if (valid[r]) out[m] = finalize_row(make_double2(e_re[r], e_im[r]), psi, psi_dtype, m);
     }
 }
 

@@ -223,31 +223,38 @@ constexpr int kLookDense = 0, kLookHash = 1;
 // is consumed (memory-level parallelism); lanes whose H is exactly 0.0 (hamiltonian.py:363) or whose coupled
 // state leaves the sector (hamiltonian.py:328) read entry 0 / slot 0 instead — a single broadcast sector —
 // and contribute H * psi = 0 exactly, so no branch is needed.
+// 64-bit address of entry `key` of the dense table with ONE instruction (IMAD.WIDE.U32 on the FMA pipe)
+__device__ __forceinline__ const double2* dense_entry(const double2* __restrict__ base, uint32_t key) {
+    unsigned long long addr;
+    asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(addr) : "r"(key), "l"(base));
+    return reinterpret_cast<const double2*>(addr);
+}
+
 template <int NW, bool SEC, bool KEYORDER, int B>
-__device__ __forceinline__ void emit_batch(const double (&h)[B], const uint32_t* __restrict__ U, int u_stride, const uint32_t (&s)[NW],
+__device__ __forceinline__ void emit_batch(const double (&h)[B], const uint32_t (&u)[B], const uint32_t (&s)[NW],
                                            bool valid, const Sector& sec, const LookupView& lv, double& e_re, double& e_im) {
+    static_assert(NW == 1, "the dense lookup holds keys of <= 30 bits");
     double hh[B];
-    {
-        double2 p[B];
+    double2 p[B];
 #pragma unroll
-        for (int b = 0; b < B; ++b) {
-            uint32_t j[NW];
-#pragma unroll
-            for (int w = 0; w < NW; ++w) j[w] = s[w] ^ U[b * u_stride + w];
+    for (int b = 0; b < B; ++b) {
+        const uint32_t j[1] = {s[0] ^ u[b]};
+        if constexpr (KEYORDER && !SEC) {
+            // key-order walk: the 32 lanes hold 32 consecutive keys, so s ^ u stays inside one aligned 32-entry block of
+            // the table for every lane — loading it even where h == 0 costs no extra line and needs neither test nor select
+            p[b] = __ldg(dense_entry(lv.dense, j[0]));
+            hh[b] = h[b];
+        } else {
             bool on = (h[b] != 0.0) & valid;
-            if constexpr (SEC) on = on && in_sector<NW>(j, sec);
-            unsigned long long k0, k1;
-            key_words64<NW>(j, k0, k1);
-            // key-order mode: the 32 lanes hold 32 consecutive keys, so s ^ u stays inside one aligned 32-entry block of
-            // the table for every lane — loading it even where h == 0 costs no extra line, and needs no select
-            p[b] = __ldg(lv.dense + ((KEYORDER || on) ? k0 : 0ull));
+            if constexpr (SEC) on = on && in_sector<1>(j, sec);
+            p[b] = __ldg(dense_entry(lv.dense, (KEYORDER || on) ? j[0] : 0u));
             hh[b] = SEC ? (on ? h[b] : 0.0) : h[b];  // without a sector filter "off" already means h == 0 (or an invalid lane)
         }
+    }
 #pragma unroll
-        for (int b = 0; b < B; ++b) {
-            e_re = __fma_rn(hh[b], p[b].x, e_re);
-            e_im = __fma_rn(hh[b], p[b].y, e_im);
-        }
+    for (int b = 0; b < B; ++b) {
+        e_re = __fma_rn(hh[b], p[b].x, e_re);
+        e_im = __fma_rn(hh[b], p[b].y, e_im);
     }
 }
 
@@ -257,7 +264,8 @@ __device__ __forceinline__ void emit_batch(const double (&h)[B], const uint32_t*
 // of all B couplings are issued before any is examined, so their L2 latencies overlap.
 template <int NW, bool SEC, int B>
 __device__ __forceinline__ void heavy_lookup(int n, const double (&h)[B], const uint32_t* const (&u)[B], const uint32_t (&s)[NW],
-                                             const Sector& sec, const LookupView& lv, double& e_re, double& e_im) {
+                                             const Sector& sec, const LookupView& lv, const uint32_t* __restrict__ sfilt,
+                                             double& e_re, double& e_im) {
     unsigned long long k0[B], k1[B];
     unsigned slot[B];
     bool on[B];
@@ -269,7 +277,17 @@ __device__ __forceinline__ void heavy_lookup(int n, const double (&h)[B], const 
         for (int w = 0; w < NW; ++w) j[w] = on[b] ? (s[w] ^ u[b][w]) : s[w];
         if constexpr (SEC) on[b] = on[b] && in_sector<NW>(j, sec);
         key_words64<NW>(j, k0[b], k1[b]);
-        slot[b] = NW <= 2 ? (hash32(k0[b], 0ull) >> lv.bshift) : (unsigned)hash_slot(k0[b], k1[b], lv.shift);
+        if constexpr (NW <= 2) {
+            const uint32_t hh = hash32(k0[b], 0ull);
+            slot[b] = hh >> lv.bshift;
+            if (sfilt) {  // a clear bit proves the key is not in the table: no global access at all
+                uint32_t b1, b2;
+                filter_positions(hh, b1, b2);
+                on[b] = on[b] && ((sfilt[b1 >> 5] >> (b1 & 31)) & (sfilt[b2 >> 5] >> (b2 & 31)) & 1u);
+            }
+        } else {
+            slot[b] = (unsigned)hash_slot(k0[b], k1[b], lv.shift);
+        }
     }
     if constexpr (NW <= 2) {
         // bucketed table: the 4 keys of a bucket are one sector; all B first probes are in flight together
@@ -328,7 +346,7 @@ constexpr int kQueueCap = 16;  // pending couplings per thread (hash mode)
 // read of a group falls into one aligned 512-byte block: 4 L1 lines per request instead of ~11 scattered sectors.
 template <int NW, int NN, int THREADS, int LK, bool SEC, bool KEYORDER>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
-eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint32_t queue_offset, Sector sec, LookupView lv,
+eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint32_t queue_offset, uint32_t filter_offset, Sector sec, LookupView lv,
                    const uint64_t* __restrict__ states, const uint32_t* __restrict__ need, const void* __restrict__ psi,
                    int psi_dtype, int64_t M, double2* __restrict__ out, double2* __restrict__ partial) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -342,6 +360,15 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const uint32_t* sfilt = nullptr;  // Bloom filter of the table keys in shared memory (hash lookup, 1024-thread shape)
+    if constexpr (LK == kLookHash) {
+        if (lv.filter) {
+            uint4* dst = reinterpret_cast<uint4*>(smem + filter_offset);
+            const uint4* src = reinterpret_cast<const uint4*>(lv.filter);
+            for (uint32_t i = threadIdx.x; i < kFilterBytes / 16; i += THREADS) dst[i] = __ldg(src + i);
+            sfilt = reinterpret_cast<const uint32_t*>(smem + filter_offset);
+        }
     }
     __syncthreads();
     uint32_t phase0 = 0, phase1 = 0;
@@ -396,7 +423,7 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                 }
             }
             qcnt -= n;
-            heavy_lookup<NW, SEC, PB>(n, h, u, s, sec, lv, e_re, e_im);
+            heavy_lookup<NW, SEC, PB>(n, h, u, s, sec, lv, sfilt, e_re, e_im);
         };
         // branch-free: the entry is always written at the tail, the tail only advances for a live coupling
         auto push = [&](double h, uint32_t lut_off8, uint32_t u_off4) {
@@ -412,6 +439,8 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                     const uint32_t* U = reinterpret_cast<const uint32_t*>(rec + 64 * NN);
                     const unsigned char* L = rec + 64 * NN + 32 * NW;
                     if constexpr (LK == kLookDense) {
+                        const uint4 ua = *reinterpret_cast<const uint4*>(U), ub = *reinterpret_cast<const uint4*>(U + 4);
+                        const uint32_t uu[2][4] = {{ua.x, ua.y, ua.z, ua.w}, {ub.x, ub.y, ub.z, ub.w}};
 #pragma unroll
                         for (int j0 = 0; j0 < 8; j0 += 4) {
                             double h[4];
@@ -421,7 +450,7 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                                 const uint32_t off = j == 0 ? ((P << 3) & 0x78u) : ((P >> (4 * j - 3)) & 0x78u);
                                 h[jj] = *reinterpret_cast<const double*>(L + j * 128 + off);
                             }
-                            emit_batch<NW, SEC, KEYORDER, 4>(h, U + j0 * NW, NW, s, valid, sec, lv, e_re, e_im);
+                            emit_batch<NW, SEC, KEYORDER, 4>(h, uu[j0 / 4], s, valid, sec, lv, e_re, e_im);
                         }
                     } else {
 #pragma unroll
@@ -441,13 +470,15 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                     const uint32_t* U = reinterpret_cast<const uint32_t*>(rec + 64 * NN);
                     const unsigned char* L = rec + 64 * NN + 32 * NW;
                     if constexpr (LK == kLookDense) {
+                        const uint4 ua = *reinterpret_cast<const uint4*>(U);
+                        const uint32_t uu[5] = {ua.x, ua.y, ua.z, ua.w, U[4]};
                         double h[5];
 #pragma unroll
                         for (int j = 0; j < 5; ++j) {
                             const uint32_t off = j == 0 ? ((P << 3) & 0x1f8u) : ((P >> (6 * j - 3)) & 0x1f8u);
                             h[j] = *reinterpret_cast<const double*>(L + j * 512 + off);
                         }
-                        emit_batch<NW, SEC, KEYORDER, 5>(h, U, NW, s, valid, sec, lv, e_re, e_im);
+                        emit_batch<NW, SEC, KEYORDER, 5>(h, uu, s, valid, sec, lv, e_re, e_im);
                     } else {
 #pragma unroll
                         const uint32_t l8 = (uint32_t)(L - buf) >> 3, u4 = (uint32_t)(reinterpret_cast<const unsigned char*>(U) - buf) >> 2;
@@ -478,19 +509,25 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                         for (uint32_t sb = 0; sb < nsb; ++sb) {
                             const uint32_t Db = D >> (8 * sb);
 #pragma unroll
-                            for (int t = 0; t < 8; ++t) {
-                                const int hi = __double2hiint(acc) ^ (int)((Db << (31 - t)) & 0x80000000u);
-                                acc = __dadd_rn(__hiloint2double(hi, __double2loint(acc)), C[sb * 8 + t]);
+                            for (int t = 0; t < 8; t += 2) {
+                                const double2 cc = *reinterpret_cast<const double2*>(C + sb * 8 + t);  // one LDS.128, two terms
+                                int hi = __double2hiint(acc) ^ (int)((Db << (31 - t)) & 0x80000000u);
+                                acc = __dadd_rn(__hiloint2double(hi, __double2loint(acc)), cc.x);
+                                hi = __double2hiint(acc) ^ (int)((Db << (30 - t)) & 0x80000000u);
+                                acc = __dadd_rn(__hiloint2double(hi, __double2loint(acc)), cc.y);
                             }
                         }
                         if (nsb < 4) flip = (P << (8 * (4 - nsb))) & 0x80000000u;  // sign of the last processed term
                     }
                     if (flags & kBlobLast) {
                         double h[1] = {__hiloint2double(__double2hiint(acc) ^ (int)flip, __double2loint(acc))};
-                        if constexpr (LK == kLookDense) emit_batch<NW, SEC, KEYORDER, 1>(h, hdr + 4, NW, s, valid, sec, lv, e_re, e_im);
+                        if constexpr (LK == kLookDense) {
+                            const uint32_t u1[1] = {hdr[4]};
+                            emit_batch<NW, SEC, KEYORDER, 1>(h, u1, s, valid, sec, lv, e_re, e_im);
+                        }
                         else {
                             const uint32_t* uu[1] = {hdr + 4};
-                            heavy_lookup<NW, SEC, 1>((h[0] != 0.0 && valid) ? 1 : 0, h, uu, s, sec, lv, e_re, e_im);
+                            heavy_lookup<NW, SEC, 1>((h[0] != 0.0 && valid) ? 1 : 0, h, uu, s, sec, lv, sfilt, e_re, e_im);
                         }
                     }
                     p += kBlobHeader + (size_t)n_words * REC_C;
@@ -516,7 +553,7 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
 
         if (valid) {
             if (KEYORDER || partial) partial[(int64_t)blockIdx.y * M + m] = make_double2(e_re, e_im);
-            else out[m] = div_conj(make_double2(e_re, e_im), load_psi(psi, psi_dtype, m));
+            else out[m] = finalize_row(make_double2(e_re, e_im), psi, psi_dtype, m);
         }
     }
 }
@@ -531,7 +568,7 @@ __global__ void eloc_finalize_kernel(const double2* __restrict__ partial, int n_
         const double2 p = partial[(int64_t)c * M + m];
         re = __dadd_rn(re, p.x); im = __dadd_rn(im, p.y);
     }
-    out[m] = div_conj(make_double2(re, im), load_psi(psi, psi_dtype, m));
+    out[m] = finalize_row(make_double2(re, im), psi, psi_dtype, m);
 }
 
 // key-order mode helpers: mark the keys that occur as rows; gather S[key_m] per row, divide and conjugate
@@ -553,7 +590,7 @@ __global__ void eloc_rows_finalize_kernel(const double2* __restrict__ partial, i
         const double2 p = partial[(int64_t)c * n_keys + k];
         re = __dadd_rn(re, p.x); im = __dadd_rn(im, p.y);
     }
-    out[m] = div_conj(make_double2(re, im), load_psi(psi, psi_dtype, m));
+    out[m] = finalize_row(make_double2(re, im), psi, psi_dtype, m);
 }
 
 }  // namespace naqs

@@ -96,6 +96,15 @@ __global__ void bucket_insert_kernel(HashBucket* buckets, unsigned bmask, int bs
     }
 }
 
+__global__ void filter_build_kernel(uint32_t* filter, const uint64_t* __restrict__ keys, int words, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t b1, b2;
+    filter_positions(hash32(keys[i * words], 0ull), b1, b2);
+    atomicOr(&filter[b1 >> 5], 1u << (b1 & 31));
+    atomicOr(&filter[b2 >> 5], 1u << (b2 & 31));
+}
+
 __global__ void dense_scatter_kernel(double2* dense, const uint64_t* __restrict__ keys, const void* __restrict__ psi,
                                      int psi_dtype, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -112,7 +121,7 @@ constexpr int kThreads = 256;
 // sliced kernel launch shapes: threads per CTA and shared-memory tile capacity (two buffers per CTA)
 constexpr int kSlicedThreads[3] = {1024, 512, 256};
 // tile capacities: [0..2] dense lookup, [3..5] hash lookup (which also keeps a 64 B/thread coupling queue in smem)
-constexpr size_t kSlicedCap[6] = {112640, 55296, 26624, 79872, 36864, 18432};
+constexpr size_t kSlicedCap[6] = {112640, 55296, 26624, 47104, 36864, 18432};  // hash/1024: 2 x 46 KB tiles + 64 KB queue + 64 KB filter
 constexpr size_t kSlicedMaxBlob = 16384;
 
 static int tile_cap_for(int nw32, int64_t K) {
@@ -264,7 +273,7 @@ int naqs_table_destroy(naqs_table_t* t) {
     if (!t) return NAQS_OK;
     DeviceGuard guard(t->device);
     cudaFree(t->d_yz); cudaFree(t->d_coeff); cudaFree(t->d_gxy); cudaFree(t->d_gstart);
-    cudaFree(t->d_dense); cudaFree(t->d_slots); cudaFree(t->d_buckets); cudaFree(t->d_ws); cudaFree(t->d_stage);
+    cudaFree(t->d_dense); cudaFree(t->d_slots); cudaFree(t->d_buckets); cudaFree(t->d_filter); cudaFree(t->d_ws); cudaFree(t->d_stage);
     if (t->h_pinned) cudaFreeHost(t->h_pinned);
     if (t->own_stream) cudaStreamDestroy(t->own_stream);
     cudaFree(t->d_tiles); cudaFree(t->d_binom); cudaFree(t->d_stream); cudaFree(t->d_partial);
@@ -290,6 +299,7 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
     if (kind == NAQS_LOOKUP_AUTO) kind = (t->n_qubits <= 22) ? NAQS_LOOKUP_DENSE : NAQS_LOOKUP_HASH;
     NAQS_REQUIRE(kind == NAQS_LOOKUP_DENSE || kind == NAQS_LOOKUP_HASH, NAQS_ERR_ARG, "naqs_lookup_build: bad kind");
     const int blocks = (int)((n + 255) / 256);
+    if (kind == NAQS_LOOKUP_DENSE || t->nw32 > 2) t->filter_valid = false;
     if (kind == NAQS_LOOKUP_DENSE) {
         NAQS_REQUIRE(t->n_qubits <= 30, NAQS_ERR_ARG, "naqs_lookup_build: dense lookup needs n_qubits <= 30");
         const int64_t entries = 1ll << t->n_qubits;
@@ -321,6 +331,14 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
             const LookupView lv = t->lookup();
             bucket_insert_kernel<<<blocks, 256, 0, stream>>>(t->d_buckets, lv.bmask, lv.bshift, d_keys, t->words, d_psi, psi_dtype, n);
             NAQS_LAUNCHED();
+        }
+        t->filter_valid = false;
+        if (n > 0 && n * 4 <= (int64_t)kFilterBits && !getenv("NAQS_ELOC_NO_FILTER")) {
+            if (!t->d_filter) NAQS_CUDA(cudaMalloc((void**)&t->d_filter, kFilterBytes));
+            NAQS_CUDA(cudaMemsetAsync(t->d_filter, 0, kFilterBytes, stream));
+            filter_build_kernel<<<blocks, 256, 0, stream>>>(t->d_filter, d_keys, t->words, n);
+            NAQS_LAUNCHED();
+            t->filter_valid = true;
         }
     } else {
         // load factor <= 0.25 while the table stays well inside L2 (32 B slots), else <= 0.5
@@ -379,9 +397,15 @@ static int launch_sliced_cfg(naqs_table_t* t, const uint64_t* d_states, const vo
     const bool resident = tiles_per_chunk <= 1;
     const size_t queue_bytes = LK == kLookHash ? (size_t)kQueueCap * 4 * THREADS : 0;
     const size_t queue_offset = resident ? cap : 2 * cap;
-    const size_t smem = queue_offset + queue_bytes;
+    // the Bloom filter rides along only in the 1-CTA-per-SM shape (it needs 64 KB of shared memory)
+    const bool use_filter = LK == kLookHash && CFG == 0 && t->filter_valid;
+    const size_t filter_offset = queue_offset + queue_bytes;
+    const size_t smem = filter_offset + (use_filter ? kFilterBytes : 0);
     auto kern = eloc_sliced_kernel<NW, NN, THREADS, LK, SEC, KEYORDER>;
-    NAQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * cap + queue_bytes)));
+    NAQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(2 * cap + queue_bytes + (LK == kLookHash && CFG == 0 ? kFilterBytes : 0))));
+    LookupView lv = t->lookup();
+    if (!use_filter) lv.filter = nullptr;
     double2* partial = nullptr;
     uint32_t* need_bits = nullptr;
     if (n_chunks > 1 || KEYORDER) {
@@ -404,7 +428,7 @@ static int launch_sliced_cfg(naqs_table_t* t, const uint64_t* d_states, const vo
     const int slots = sm_count * (1024 / THREADS);
     dim3 grid((unsigned)std::min<int64_t>(n_blocks, slots), (unsigned)n_chunks);
     SlicedView sv{t->d_stream, (const STile*)t->d_stiles[TL], n_tiles, t->nn};
-    kern<<<grid, THREADS, smem, stream>>>(sv, tiles_per_chunk, (uint32_t)cap, (uint32_t)queue_offset, t->sector, t->lookup(), d_states, need_bits, d_psi, psi_dtype,
+    kern<<<grid, THREADS, smem, stream>>>(sv, tiles_per_chunk, (uint32_t)cap, (uint32_t)queue_offset, (uint32_t)filter_offset, t->sector, lv, d_states, need_bits, d_psi, psi_dtype,
                                           M, reinterpret_cast<double2*>(d_eloc), partial);
     NAQS_LAUNCHED();
     if (KEYORDER) {
@@ -514,6 +538,29 @@ int naqs_eloc(naqs_table_t* t, const uint64_t* d_states, const void* d_psi, int 
         case 1: return launch_eloc<1>(t, d_states, d_psi, psi_dtype, M, d_eloc, stream);
         case 2: return launch_eloc<2>(t, d_states, d_psi, psi_dtype, M, d_eloc, stream);
         default: return launch_eloc<4>(t, d_states, d_psi, psi_dtype, M, d_eloc, stream);
+    }
+}
+
+int naqs_apply_h(naqs_table_t* t, const uint64_t* d_states, int64_t M, double* d_out, void* stream_) {
+    NAQS_REQUIRE(t, NAQS_ERR_ARG, "naqs_apply_h: NULL table");
+    NAQS_REQUIRE(M >= 0 && (M == 0 || (d_states && d_out)), NAQS_ERR_ARG, "naqs_apply_h: NULL buffers");
+    NAQS_REQUIRE(t->lookup_kind != 0, NAQS_ERR_STATE, "naqs_apply_h: call naqs_lookup_build first (it holds the vector)");
+    if (M == 0) return NAQS_OK;
+    // same kernels as naqs_eloc; a NULL psi makes the finalisation write the raw row sums
+    DeviceGuard guard(t->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (t->algo == 0) {
+        switch (t->nn) {
+            case 5: return launch_sliced<1, 5>(t, d_states, nullptr, NAQS_C128, M, d_out, stream);
+            case 8: return launch_sliced<1, 8>(t, d_states, nullptr, NAQS_C128, M, d_out, stream);
+            case 16: return launch_sliced<2, 16>(t, d_states, nullptr, NAQS_C128, M, d_out, stream);
+            default: return launch_sliced<4, 32>(t, d_states, nullptr, NAQS_C128, M, d_out, stream);
+        }
+    }
+    switch (t->nw32) {
+        case 1: return launch_eloc<1>(t, d_states, nullptr, NAQS_C128, M, d_out, stream);
+        case 2: return launch_eloc<2>(t, d_states, nullptr, NAQS_C128, M, d_out, stream);
+        default: return launch_eloc<4>(t, d_states, nullptr, NAQS_C128, M, d_out, stream);
     }
 }
 

@@ -91,6 +91,25 @@ class PauliHamiltonianB200:
         out = self.table.local_energy(np.asarray(states_idx).reshape(-1) if not torch.is_tensor(states_idx) else states_idx.reshape(-1), psi)
         return _lib.complex_from_pairs(out) if ret_numpy else out
 
+    def linear_operator(self, states_idx):
+        """scipy LinearOperator of H restricted to the given basis states, applied matrix-free on the device."""
+        from scipy.sparse.linalg import LinearOperator
+        keys = self.table._keys(np.asarray(states_idx).reshape(-1) if not torch.is_tensor(states_idx) else states_idx.reshape(-1))
+        n = keys.shape[0]
+
+        def matvec(v):
+            v = np.asarray(v).reshape(-1)
+            out = _lib.complex_from_pairs(self.table.apply_H(keys, v.astype(np.complex128)))
+            return out if np.iscomplexobj(v) else out.real
+
+        return LinearOperator((n, n), matvec=matvec, dtype=np.float64)
+
+    def solve_H(self, states_idx, k=1, tol=1e-10):
+        """Lowest eigenpairs of H on the sub-space spanned by `states_idx` (what OptimizerBase.solve_H computes with
+        scipy eigs on the cached CSR, energy.py:762-786) by Lanczos on the matrix-free operator."""
+        from scipy.sparse.linalg import eigsh
+        return eigsh(self.linear_operator(states_idx), k=k, which="SA", tol=tol)
+
     # ------------------------------------------------------------------ reference API
     def _rows_csr(self, state_i_idx):
         indptr, cols, ridx, vals = self.table.rows(state_i_idx.astype(np.int64), with_restricted_index=True)

@@ -98,6 +98,17 @@ class DeviceTermTable:
             _lib.check(_lib.load().naqs_eloc(self._h, _lib.ptr(k), _lib.ptr(p), code, M, _lib.ptr(out), self._stream()), "naqs_eloc")
         return out
 
+    def apply_H(self, states, v, out=None):
+        """Matrix-free (H v)[rows]: H restricted to the basis `states`, v complex on that basis -> CUDA float64 [M, 2].
+        No matrix is formed; one fused kernel per application (naqs_lookup_build holds v, naqs_apply_h walks the rows)."""
+        k = self._keys(states)
+        self.build_lookup(k, v)
+        if out is None:
+            out = torch.empty((k.shape[0], 2), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().naqs_apply_h(self._h, _lib.ptr(k), k.shape[0], _lib.ptr(out), self._stream()), "naqs_apply_h")
+        return out
+
     def local_energy_host(self, states, psi, table_keys=None, table_psi=None, out=None):
         """Host-buffer path (numpy in, numpy complex128 out) through naqs_eloc_host: upload -> lookup build -> fused
         kernel -> download, synchronous.  Page-locked inputs / `out` (e.g. numpy views of pinned torch tensors) make the
