@@ -173,6 +173,16 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def ncu_summary():
+    """Per-workload ncu figures of the hot kernel (dram bytes per launch, L1TEX / issue utilisation), profiles/ncu_summary_rNN.json."""
+    d = os.path.join(ROOT, "profiles")
+    for name in sorted(os.listdir(d), reverse=True) if os.path.isdir(d) else []:
+        if name.startswith("ncu_summary") and name.endswith(".json"):
+            with open(os.path.join(d, name)) as f:
+                return json.load(f)
+    return {}
+
+
 def pipe_peaks():
     """Integer / fp64 pipe ceilings measured with bench_tools/pipe_peaks.cu on this pool's B200 (profiles/)."""
     for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True) if os.path.isdir(os.path.join(ROOT, "profiles")) else []:
@@ -374,19 +384,29 @@ def main():
     peaks, peak_src = measured_peaks()
     k_ms = float(np.mean(kern_ms))
     T = (world * M) if not dedup else int(t_keys.shape[0])
-    algo_bytes = M * (8 * W + 8 + 16) + K * (16 * W + 8) + min(T, 2 ** wl["N"]) * 16  # states+psi in, E_loc out, Pauli table, lookup entries touched
+    # algorithmic HBM bytes of one launch: states + psi in, E_loc out, Pauli table, lookup entries touched once
+    algo_bytes = M * (8 * W + 8 + 16) + K * (16 * W + 8) + min(T, 2 ** min(wl["N"], 40)) * 16
     achieved_gbs = algo_bytes / (k_ms * 1e-3) / 1e9
+    ncu = ncu_summary().get(args.workload, {})
+    traffic = (ncu.get("dram_bytes_read", 0) + ncu.get("dram_bytes_write", 0)) if ncu else None
     roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"],
-                "traffic": None, "peak_source": peak_src, "kernel": "eloc_direct_kernel", "kernel_ms": k_ms,
-                "note": "HBM is not the binding resource (0.03 B/coupling, SURVEY.md §8d); see roofline_pipe"}
+                "traffic": traffic, "peak_source": peak_src, "kernel": "eloc_sliced_kernel (+ mark_keys / rows_finalize in key-order mode)",
+                "kernel_ms": k_ms, "algorithmic_bytes": int(algo_bytes),
+                "note": "HBM is NOT the binding resource of this path (0.03 B per coupling, SURVEY.md §8d): the kernel is bound by L1TEX "
+                        "wavefronts (shared-memory LUT reads + table gathers) and warp-instruction issue; see roofline_pipe"}
     pp, pp_name = pipe_peaks()
     kernel_rate = M * K / (k_ms * 1e-3)
-    roofline_pipe = {"kernel_couplings_per_s": kernel_rate, "peak": None, "frac": None}
+    roofline_pipe = {"kernel_couplings_per_s": kernel_rate, "unit": UNIT}
     if pp:
-        roofline_pipe = {"bound": "popc+issue (direct formulation: AND, POPC, SHL, XOR, DADD per coupling)",
-                         "kernel_couplings_per_s": kernel_rate, "peak": pp.get("direct_couplings_per_s"), "unit": UNIT,
-                         "frac": kernel_rate / pp["direct_couplings_per_s"] if pp.get("direct_couplings_per_s") else None,
-                         "popc_ops_per_s": pp.get("popc_ops_per_s"), "dadd_ops_per_s": pp.get("dadd_ops_per_s"), "peak_source": f"profiles/{pp_name}"}
+        roofline_pipe.update({"direct_formulation_ceiling": pp.get("direct_couplings_per_s"),
+                              "vs_direct_ceiling": kernel_rate / pp["direct_couplings_per_s"] if pp.get("direct_couplings_per_s") else None,
+                              "popc_ops_per_s": pp.get("popc_ops_per_s"), "dadd_ops_per_s": pp.get("dadd_ops_per_s"),
+                              "gather16B_L2_per_s": pp.get("gather16B_16MB_per_s"), "peak_source": f"profiles/{pp_name}"})
+    if ncu:
+        roofline_pipe.update({"bound": "l1tex_wavefronts" if ncu["l1tex_data_pipe_pct"] >= ncu["issue_active_pct"] else "issue",
+                              "l1tex_data_pipe_pct_ncu": ncu["l1tex_data_pipe_pct"], "issue_active_pct_ncu": ncu["issue_active_pct"],
+                              "frac": max(ncu["l1tex_data_pipe_pct"], ncu["issue_active_pct"]) / 100.0,
+                              "ncu_source": ncu.get("source")})
     cpu = None
     if world == 1 and args.cpu_sample > 0:
         try:

@@ -406,34 +406,35 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
         // 32-bit word each: LUT entry offset | flip-mask offset inside the current tile) and resolved in warp-wide
         // rounds, so the expensive part (sector test, hashing, probing) runs with most lanes busy although only a
         // fraction of the (state, group) pairs couples.  The queue is drained before a tile buffer is released.
-        uint32_t qcnt = 0;
-        uint32_t* const q = reinterpret_cast<uint32_t*>(smem + queue_offset) + threadIdx.x;
+        constexpr uint32_t QSTRIDE = THREADS * 4;  // bytes between consecutive queue slots of one thread
+        unsigned char* const q0 = smem + queue_offset + threadIdx.x * 4;
+        unsigned char* qtail = q0;            // the queue holds (qtail - q0) / QSTRIDE couplings
         constexpr int PB = 4;  // couplings resolved per thread and round
         auto pop_round = [&](const unsigned char* __restrict__ buf) {
-            const int n = min((int)qcnt, PB);
+            const int n = min((int)((uint32_t)(qtail - q0) / QSTRIDE), PB);
             double h[PB];
             const uint32_t* u[PB];
 #pragma unroll
             for (int b = 0; b < PB; ++b) {
                 h[b] = 0.0; u[b] = reinterpret_cast<const uint32_t*>(buf);
                 if (b < n) {
-                    const uint32_t e = q[(qcnt - 1 - b) * THREADS];
+                    const uint32_t e = *reinterpret_cast<const uint32_t*>(qtail - (b + 1) * QSTRIDE);
                     h[b] = *reinterpret_cast<const double*>(buf + (e & 0xffffu) * 8u);
                     u[b] = reinterpret_cast<const uint32_t*>(buf + (e >> 16) * 4u);
                 }
             }
-            qcnt -= n;
+            qtail -= n * QSTRIDE;
             heavy_lookup<NW, SEC, PB>(n, h, u, s, sec, lv, sfilt, e_re, e_im);
         };
         // branch-free: the entry is always written at the tail, the tail only advances for a live coupling
-        auto push = [&](double h, uint32_t lut_off8, uint32_t u_off4) {
-            q[qcnt * THREADS] = lut_off8 | (u_off4 << 16);
-            qcnt += (h != 0.0 && valid) ? 1u : 0u;
+        auto push = [&](double h, uint32_t entry) {
+            *reinterpret_cast<uint32_t*>(qtail) = entry;
+            if (h != 0.0 && valid) qtail += QSTRIDE;
         };
 
-        auto process = [&](const unsigned char* __restrict__ buf, const STile& tl) {
-            if (tl.kind == kSecA) {
-                for (uint32_t r = 0; r < tl.count; ++r) {
+        auto process = [&](const unsigned char* __restrict__ buf, const uint32_t tl_kind, const uint32_t tl_count) {
+            if (tl_kind == kSecA) {
+                for (uint32_t r = 0; r < tl_count; ++r) {
                     const unsigned char* rec = buf + (size_t)r * REC_A;
                     const uint32_t P = parity_word<NN>(rec, nib);
                     const uint32_t* U = reinterpret_cast<const uint32_t*>(rec + 64 * NN);
@@ -454,17 +455,18 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                         }
                     } else {
 #pragma unroll
-                        const uint32_t l8 = (uint32_t)(L - buf) >> 3, u4 = (uint32_t)(reinterpret_cast<const unsigned char*>(U) - buf) >> 2;
+                        // entry = (LUT entry offset / 8) | (flip-mask offset / 4) << 16, both relative to the tile buffer
+                        const uint32_t ebase = ((uint32_t)(L - buf) >> 3) | (((uint32_t)(reinterpret_cast<const unsigned char*>(U) - buf) >> 2) << 16);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const uint32_t off = j == 0 ? ((P << 3) & 0x78u) : ((P >> (4 * j - 3)) & 0x78u);
-                            push(*reinterpret_cast<const double*>(L + j * 128 + off), l8 + j * 16 + (off >> 3), u4 + j * NW);
+                            const uint32_t idx = (P >> (4 * j)) & 15u;
+                            push(*reinterpret_cast<const double*>(L + j * 128 + idx * 8), ebase + j * (16u + ((uint32_t)NW << 16)) + idx);
                         }
-                        while (__any_sync(0xffffffffu, qcnt > kQueueCap - 8)) pop_round(buf);
+                        while (__any_sync(0xffffffffu, qtail > q0 + (kQueueCap - 8) * QSTRIDE)) pop_round(buf);
                     }
                 }
-            } else if (tl.kind == kSecB) {
-                for (uint32_t r = 0; r < tl.count; ++r) {
+            } else if (tl_kind == kSecB) {
+                for (uint32_t r = 0; r < tl_count; ++r) {
                     const unsigned char* rec = buf + (size_t)r * REC_B;
                     const uint32_t P = parity_word<NN>(rec, nib);
                     const uint32_t* U = reinterpret_cast<const uint32_t*>(rec + 64 * NN);
@@ -481,18 +483,18 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                         emit_batch<NW, SEC, KEYORDER, 5>(h, uu, s, valid, sec, lv, e_re, e_im);
                     } else {
 #pragma unroll
-                        const uint32_t l8 = (uint32_t)(L - buf) >> 3, u4 = (uint32_t)(reinterpret_cast<const unsigned char*>(U) - buf) >> 2;
+                        const uint32_t ebase = ((uint32_t)(L - buf) >> 3) | (((uint32_t)(reinterpret_cast<const unsigned char*>(U) - buf) >> 2) << 16);
 #pragma unroll
                         for (int j = 0; j < 5; ++j) {
-                            const uint32_t off = j == 0 ? ((P << 3) & 0x1f8u) : ((P >> (6 * j - 3)) & 0x1f8u);
-                            push(*reinterpret_cast<const double*>(L + j * 512 + off), l8 + j * 64 + (off >> 3), u4 + j * NW);
+                            const uint32_t idx = (P >> (6 * j)) & 63u;
+                            push(*reinterpret_cast<const double*>(L + j * 512 + idx * 8), ebase + j * (64u + ((uint32_t)NW << 16)) + idx);
                         }
-                        while (__any_sync(0xffffffffu, qcnt > kQueueCap - 8)) pop_round(buf);
+                        while (__any_sync(0xffffffffu, qtail > q0 + (kQueueCap - 8) * QSTRIDE)) pop_round(buf);
                     }
                 }
             } else {
                 const unsigned char* p = buf;
-                for (uint32_t b = 0; b < tl.count; ++b) {
+                for (uint32_t b = 0; b < tl_count; ++b) {
                     const uint32_t* hdr = reinterpret_cast<const uint32_t*>(p);
                     const uint32_t n_words = hdr[0], n_sub8 = hdr[1], flags = hdr[2];
                     if (flags & kBlobFirst) { acc = 0.0; flip = 0; }
@@ -544,9 +546,10 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                 else        { mbar_wait(&mbar[1], phase1); phase1 ^= 1; }
             }
             have_resident = resident;
-            process(smem + (size_t)b * buf_bytes, sv.tiles[t]);
+            const uint32_t tl_kind = sv.tiles[t].kind, tl_count = sv.tiles[t].count;
+            process(smem + (size_t)b * buf_bytes, tl_kind, tl_count);
             if constexpr (LK == kLookHash) {
-                while (__any_sync(0xffffffffu, qcnt > 0)) pop_round(smem + (size_t)b * buf_bytes);
+                while (__any_sync(0xffffffffu, qtail != q0)) pop_round(smem + (size_t)b * buf_bytes);
             }
             if (!resident) __syncthreads();  // every thread is done with buffer b before it is refilled
         }
