@@ -302,11 +302,11 @@ def main():
         if world > 1:
             # public multi-GPU API: all-gather (key, psi) -> lookup build -> fused E_loc on the shard -> all-reduce of 5 sums
             g_k, g_p, _ = naqs_b200.distributed.gather_table(states, psi, equal_sizes=True, out=(g_states, g_psi))
-            table.build_lookup(g_k, g_p)
+            table.build_lookup(g_k, g_p)  # gathered shards may share keys -> duplicates summed (complex128 table)
         elif dedup:
-            table.build_lookup(t_keys, t_psi)
+            table.build_lookup(t_keys, t_psi, assume_unique=True)
         else:
-            table.build_lookup(states, psi)
+            table.build_lookup(states, psi, assume_unique=True)  # distinct keys by construction (energy.py:245 contract)
         ev_k0.record()
         table.local_energy(states, psi, out=out, rebuild_lookup=False)
         ev_k1.record()
@@ -351,7 +351,7 @@ def main():
     if not args.no_e2e:
         def e2e_step():
             if world == 1 and not dedup:
-                return table.local_energy_host(h_states_np, h_psi_np, out=h_eloc_np)
+                return table.local_energy_host(h_states_np, h_psi_np, out=h_eloc_np, assume_unique=True)
             ds, dp = h_states.to(dev, non_blocking=True), h_psi.to(dev, non_blocking=True)
             step(ds, dp, d_eloc)
             h_eloc.copy_(d_eloc, non_blocking=True)

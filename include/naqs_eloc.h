@@ -45,6 +45,10 @@ enum { NAQS_C128 = 0, NAQS_C64 = 1 };
 
 /* lookup-table organisations (naqs_lookup_build `kind`; NAQS_LOOKUP_AUTO picks by n_qubits) */
 enum { NAQS_LOOKUP_AUTO = 0, NAQS_LOOKUP_DENSE = 1, NAQS_LOOKUP_HASH = 2 };
+/* OR-ed into `kind`: the caller guarantees that the keys are unique — the contract of the reference's own call
+ * update_H(states_idx, check_unseen=True, assume_unique=True) (src/optimizer/energy.py:245).  Lets the dense lookup keep
+ * complex64 amplitudes as 8-byte entries (no duplicate summation needed), halving the lines a table read touches. */
+#define NAQS_LOOKUP_ASSUME_UNIQUE 0x100
 
 typedef struct naqs_table naqs_table_t; /* opaque, device resident */
 
@@ -110,7 +114,7 @@ int naqs_table_set_algo(naqs_table_t* t, int algo);
  * reference's only mode) or T separate (key, psi) pairs. */
 int naqs_eloc_host(naqs_table_t* t, const uint64_t* h_states, const void* h_psi, int psi_dtype, int64_t n_states,
                    const uint64_t* h_table_keys, const void* h_table_psi, int64_t n_table,
-                   double* h_eloc);
+                   int lookup_kind /* NAQS_LOOKUP_* [| NAQS_LOOKUP_ASSUME_UNIQUE] */, double* h_eloc);
 
 /* ------------------------------------------------------------------------------------------
  * Stored Hamiltonian rows (CSR / coupled-set mode) — replaces update_H's row construction

@@ -14,6 +14,7 @@ from . import _build
 
 NAQS_C128, NAQS_C64 = 0, 1
 LOOKUP_AUTO, LOOKUP_DENSE, LOOKUP_HASH = 0, 1, 2
+LOOKUP_ASSUME_UNIQUE = 0x100
 _OK, _ERR_ARG, _ERR_DTYPE, _ERR_CUDA, _ERR_ALLOC, _ERR_STATE = range(6)
 
 # every symbol include/naqs_eloc.h declares: (restype, argtypes)
@@ -30,7 +31,7 @@ SIGNATURES = {
     "naqs_eloc": (_i, [_p, _p, _p, _i, _i64, _p, _p]),
     "naqs_table_set_algo": (_i, [_p, _i]),
     "naqs_apply_h": (_i, [_p, _p, _i64, _p, _p]),
-    "naqs_eloc_host": (_i, [_p, _p, _p, _i, _i64, _p, _p, _i64, _p]),
+    "naqs_eloc_host": (_i, [_p, _p, _p, _i, _i64, _p, _p, _i64, _i, _p]),
     "naqs_rows_count": (_i, [_p, _p, _i64, _p, _p]),
     "naqs_exclusive_scan": (_i, [_p, _p, _i64, _p, _p]),
     "naqs_rows_fill": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p]),

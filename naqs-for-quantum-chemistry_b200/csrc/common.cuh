@@ -111,6 +111,7 @@ struct LookupView {
     unsigned bmask;          // n_buckets - 1
     int bshift;              // 32 - log2(n_buckets)
     const uint32_t* filter;  // Bloom filter over the table keys (kFilterBits bits, 2 probes) or nullptr
+    const float2* dense32;   // [2^N] complex64 copy of the dense table (unique keys + complex64 psi only) or nullptr
 };
 
 // Bloom filter of the hash lookup: 2^19 bits = 64 KB, copied into shared memory by every CTA of the 1024-thread launch
@@ -168,6 +169,9 @@ struct naqs_table {
     int64_t lookup_n = 0;
     double2* d_dense = nullptr;
     int64_t dense_entries = 0;
+    float2* d_dense32 = nullptr;   // complex64 dense table (key-order walk with unique complex64 amplitudes)
+    int64_t dense32_entries = 0;
+    bool dense32_valid = false;
     naqs::HashSlot* d_slots = nullptr;     // 128-bit keys: 32 B slots, linear probing
     int64_t hash_cap = 0, hash_alloc = 0;
     naqs::HashBucket* d_buckets = nullptr; // <= 63-bit keys: 128 B buckets of 4
@@ -191,7 +195,7 @@ struct naqs_table {
         for (int64_t c = n_buckets; c > 1; c >>= 1) --bshift;
         return naqs::LookupView{d_dense, d_slots, (unsigned long long)(hash_cap - 1), lookup_kind, shift,
                                 d_buckets, (unsigned)(n_buckets > 0 ? n_buckets - 1 : 0), bshift,
-                                filter_valid ? d_filter : nullptr};
+                                filter_valid ? d_filter : nullptr, dense32_valid ? d_dense32 : nullptr};
     }
 };
 

@@ -230,12 +230,35 @@ __device__ __forceinline__ const double2* dense_entry(const double2* __restrict_
     return reinterpret_cast<const double2*>(addr);
 }
 
-template <int NW, bool SEC, bool KEYORDER, int B>
+__device__ __forceinline__ const float2* dense_entry32(const float2* __restrict__ base, uint32_t key) {
+    unsigned long long addr;
+    asm("mad.wide.u32 %0, %1, 8, %2;" : "=l"(addr) : "r"(key), "l"(base));
+    return reinterpret_cast<const float2*>(addr);
+}
+
+template <int NW, bool SEC, bool KEYORDER, bool PSI32, int B>
 __device__ __forceinline__ void emit_batch(const double (&h)[B], const uint32_t (&u)[B], const uint32_t (&s)[NW],
                                            bool valid, const Sector& sec, const LookupView& lv, double& e_re, double& e_im) {
     static_assert(NW == 1, "the dense lookup holds keys of <= 30 bits");
     double hh[B];
     double2 p[B];
+    if constexpr (PSI32) {
+        // complex64 table (unique keys): 32 consecutive keys read 256 B = 2 lines per request; float -> double is exact
+        float2 q[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            const uint32_t j[1] = {s[0] ^ u[b]};
+            q[b] = __ldg(dense_entry32(lv.dense32, j[0]));
+            hh[b] = h[b];
+            if constexpr (SEC) hh[b] = ((h[b] != 0.0) & valid && in_sector<1>(j, sec)) ? h[b] : 0.0;
+        }
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            e_re = __fma_rn(hh[b], (double)q[b].x, e_re);
+            e_im = __fma_rn(hh[b], (double)q[b].y, e_im);
+        }
+        return;
+    }
 #pragma unroll
     for (int b = 0; b < B; ++b) {
         const uint32_t j[1] = {s[0] ^ u[b]};
@@ -344,7 +367,7 @@ constexpr int kQueueCap = 16;  // pending couplings per thread (hash mode)
 // of the keys that occur as rows; the raw sums S[k] = sum_u H[k, k^u] psi(k^u) go to partial[chunk * M + k] and
 // eloc_rows_finalize_kernel turns them into E_loc per row.  A warp then holds 32 consecutive keys and every table
 // read of a group falls into one aligned 512-byte block: 4 L1 lines per request instead of ~11 scattered sectors.
-template <int NW, int NN, int THREADS, int LK, bool SEC, bool KEYORDER>
+template <int NW, int NN, int THREADS, int LK, bool SEC, bool KEYORDER, bool PSI32>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint32_t queue_offset, uint32_t filter_offset, Sector sec, LookupView lv,
                    const uint64_t* __restrict__ states, const uint32_t* __restrict__ need, const void* __restrict__ psi,
@@ -451,7 +474,7 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                                 const uint32_t off = j == 0 ? ((P << 3) & 0x78u) : ((P >> (4 * j - 3)) & 0x78u);
                                 h[jj] = *reinterpret_cast<const double*>(L + j * 128 + off);
                             }
-                            emit_batch<NW, SEC, KEYORDER, 4>(h, uu[j0 / 4], s, valid, sec, lv, e_re, e_im);
+                            emit_batch<NW, SEC, KEYORDER, PSI32, 4>(h, uu[j0 / 4], s, valid, sec, lv, e_re, e_im);
                         }
                     } else {
 #pragma unroll
@@ -480,7 +503,7 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                             const uint32_t off = j == 0 ? ((P << 3) & 0x1f8u) : ((P >> (6 * j - 3)) & 0x1f8u);
                             h[j] = *reinterpret_cast<const double*>(L + j * 512 + off);
                         }
-                        emit_batch<NW, SEC, KEYORDER, 5>(h, uu, s, valid, sec, lv, e_re, e_im);
+                        emit_batch<NW, SEC, KEYORDER, PSI32, 5>(h, uu, s, valid, sec, lv, e_re, e_im);
                     } else {
 #pragma unroll
                         const uint32_t ebase = ((uint32_t)(L - buf) >> 3) | (((uint32_t)(reinterpret_cast<const unsigned char*>(U) - buf) >> 2) << 16);
@@ -525,7 +548,7 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                         double h[1] = {__hiloint2double(__double2hiint(acc) ^ (int)flip, __double2loint(acc))};
                         if constexpr (LK == kLookDense) {
                             const uint32_t u1[1] = {hdr[4]};
-                            emit_batch<NW, SEC, KEYORDER, 1>(h, u1, s, valid, sec, lv, e_re, e_im);
+                            emit_batch<NW, SEC, KEYORDER, PSI32, 1>(h, u1, s, valid, sec, lv, e_re, e_im);
                         }
                         else {
                             const uint32_t* uu[1] = {hdr + 4};

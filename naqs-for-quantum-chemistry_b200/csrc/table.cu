@@ -105,6 +105,11 @@ __global__ void filter_build_kernel(uint32_t* filter, const uint64_t* __restrict
     atomicOr(&filter[b2 >> 5], 1u << (b2 & 31));
 }
 
+__global__ void dense_scatter32_kernel(float2* dense, const uint64_t* __restrict__ keys, const float2* __restrict__ psi, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dense[keys[i]] = psi[i];  // unique keys (caller's guarantee): a plain store
+}
+
 __global__ void dense_scatter_kernel(double2* dense, const uint64_t* __restrict__ keys, const void* __restrict__ psi,
                                      int psi_dtype, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -273,7 +278,7 @@ int naqs_table_destroy(naqs_table_t* t) {
     if (!t) return NAQS_OK;
     DeviceGuard guard(t->device);
     cudaFree(t->d_yz); cudaFree(t->d_coeff); cudaFree(t->d_gxy); cudaFree(t->d_gstart);
-    cudaFree(t->d_dense); cudaFree(t->d_slots); cudaFree(t->d_buckets); cudaFree(t->d_filter); cudaFree(t->d_ws); cudaFree(t->d_stage);
+    cudaFree(t->d_dense); cudaFree(t->d_dense32); cudaFree(t->d_slots); cudaFree(t->d_buckets); cudaFree(t->d_filter); cudaFree(t->d_ws); cudaFree(t->d_stage);
     if (t->h_pinned) cudaFreeHost(t->h_pinned);
     if (t->own_stream) cudaStreamDestroy(t->own_stream);
     cudaFree(t->d_tiles); cudaFree(t->d_binom); cudaFree(t->d_stream); cudaFree(t->d_partial);
@@ -296,7 +301,10 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
     NAQS_REQUIRE(psi_dtype == NAQS_C128 || psi_dtype == NAQS_C64, NAQS_ERR_DTYPE, "naqs_lookup_build: psi must be complex64 or complex128");
     DeviceGuard guard(t->device);
     cudaStream_t stream = (cudaStream_t)stream_;
+    const bool assume_unique = (kind & NAQS_LOOKUP_ASSUME_UNIQUE) != 0;
+    kind &= 0xff;
     if (kind == NAQS_LOOKUP_AUTO) kind = (t->n_qubits <= 22) ? NAQS_LOOKUP_DENSE : NAQS_LOOKUP_HASH;
+    t->dense32_valid = false;
     NAQS_REQUIRE(kind == NAQS_LOOKUP_DENSE || kind == NAQS_LOOKUP_HASH, NAQS_ERR_ARG, "naqs_lookup_build: bad kind");
     const int blocks = (int)((n + 255) / 256);
     if (kind == NAQS_LOOKUP_DENSE || t->nw32 > 2) t->filter_valid = false;
@@ -308,10 +316,28 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
             NAQS_CUDA(cudaMalloc((void**)&t->d_dense, (size_t)entries * sizeof(double2)));
             t->dense_entries = entries;
         }
-        NAQS_CUDA(cudaMemsetAsync(t->d_dense, 0, (size_t)entries * sizeof(double2), stream));
-        if (n > 0) {
-            dense_scatter_kernel<<<blocks, 256, 0, stream>>>(t->d_dense, d_keys, d_psi, psi_dtype, n);
-            NAQS_LAUNCHED();
+        // key-order walk + unique complex64 amplitudes: an 8-byte-per-entry table suffices (exact: the kernel widens
+        // float -> double, as sparse_math.pyx:33-37 does); otherwise the complex128 table with duplicate summation
+        const bool use32 = assume_unique && psi_dtype == NAQS_C64 && t->algo == 0 && n >= entries / 8 && t->n_qubits <= 26 &&
+                           !getenv("NAQS_ELOC_NO_KEYORDER") && !getenv("NAQS_ELOC_NO_DENSE32");
+        if (use32) {
+            if (t->dense32_entries < entries) {
+                cudaFree(t->d_dense32); t->d_dense32 = nullptr; t->dense32_entries = 0;
+                NAQS_CUDA(cudaMalloc((void**)&t->d_dense32, (size_t)entries * sizeof(float2)));
+                t->dense32_entries = entries;
+            }
+            NAQS_CUDA(cudaMemsetAsync(t->d_dense32, 0, (size_t)entries * sizeof(float2), stream));
+            if (n > 0) {
+                dense_scatter32_kernel<<<blocks, 256, 0, stream>>>(t->d_dense32, d_keys, reinterpret_cast<const float2*>(d_psi), n);
+                NAQS_LAUNCHED();
+            }
+            t->dense32_valid = true;
+        } else {
+            NAQS_CUDA(cudaMemsetAsync(t->d_dense, 0, (size_t)entries * sizeof(double2), stream));
+            if (n > 0) {
+                dense_scatter_kernel<<<blocks, 256, 0, stream>>>(t->d_dense, d_keys, d_psi, psi_dtype, n);
+                NAQS_LAUNCHED();
+            }
         }
     } else if (t->nw32 <= 2) {
         // bucketed table: 4 slots per 128 B bucket; load factor <= 0.25 while it stays well inside L2, else <= 0.5
@@ -383,7 +409,7 @@ static int launch_eloc(naqs_table_t* t, const uint64_t* d_states, const void* d_
     return NAQS_OK;
 }
 
-template <int NW, int NN, int CFG, int LK, bool SEC, bool KEYORDER>
+template <int NW, int NN, int CFG, int LK, bool SEC, bool KEYORDER, bool PSI32 = false>
 static int launch_sliced_cfg(naqs_table_t* t, const uint64_t* d_states, const void* d_psi, int psi_dtype, int64_t M_rows,
                              double* d_eloc, cudaStream_t stream, int n_chunks, int sm_count) {
     // key-order mode walks all 2^N keys; otherwise one thread per row
@@ -401,7 +427,7 @@ static int launch_sliced_cfg(naqs_table_t* t, const uint64_t* d_states, const vo
     const bool use_filter = LK == kLookHash && CFG == 0 && t->filter_valid;
     const size_t filter_offset = queue_offset + queue_bytes;
     const size_t smem = filter_offset + (use_filter ? kFilterBytes : 0);
-    auto kern = eloc_sliced_kernel<NW, NN, THREADS, LK, SEC, KEYORDER>;
+    auto kern = eloc_sliced_kernel<NW, NN, THREADS, LK, SEC, KEYORDER, PSI32>;
     NAQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)(2 * cap + queue_bytes + (LK == kLookHash && CFG == 0 ? kFilterBytes : 0))));
     LookupView lv = t->lookup();
@@ -449,8 +475,8 @@ static int launch_sliced(naqs_table_t* t, const uint64_t* d_states, const void* 
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, t->device);
     // key-order mode: dense (direct-address) lookup and a batch that covers at least 1/8 of the key space
-    const bool keyorder = NW == 1 && t->lookup_kind == NAQS_LOOKUP_DENSE && t->n_qubits <= 26 && M >= (1ll << t->n_qubits) / 8 &&
-                          !getenv("NAQS_ELOC_NO_KEYORDER");
+    const bool keyorder = NW == 1 && t->lookup_kind == NAQS_LOOKUP_DENSE && t->n_qubits <= 26 &&
+                          (t->dense32_valid || (M >= (1ll << t->n_qubits) / 8 && !getenv("NAQS_ELOC_NO_KEYORDER")));
     const int64_t M_rows = M;
     if (keyorder) M = 1ll << t->n_qubits;  // launch shape is chosen for the number of threads that actually run
     // pick the launch shape: large CTAs when there are at least two waves of them, else smaller CTAs, and split the
@@ -477,14 +503,20 @@ static int launch_sliced(naqs_table_t* t, const uint64_t* d_states, const void* 
     const bool hash = t->lookup_kind == NAQS_LOOKUP_HASH, secf = t->sector.enabled != 0;
     if constexpr (NW == 1) {
         if (keyorder) {
-#define NAQS_KO(CFG, SEC) launch_sliced_cfg<NW, NN, CFG, kLookDense, SEC, true>(t, d_states, d_psi, psi_dtype, M_rows, d_eloc, stream, n_chunks, sm_count)
-            switch (cfg * 2 + (secf ? 1 : 0)) {
-                case 0: return NAQS_KO(0, false);
-                case 1: return NAQS_KO(0, true);
-                case 2: return NAQS_KO(1, false);
-                case 3: return NAQS_KO(1, true);
-                case 4: return NAQS_KO(2, false);
-                default: return NAQS_KO(2, true);
+#define NAQS_KO(CFG, SEC, P32) launch_sliced_cfg<NW, NN, CFG, kLookDense, SEC, true, P32>(t, d_states, d_psi, psi_dtype, M_rows, d_eloc, stream, n_chunks, sm_count)
+            switch (cfg * 4 + (secf ? 2 : 0) + (t->dense32_valid ? 1 : 0)) {
+                case 0: return NAQS_KO(0, false, false);
+                case 1: return NAQS_KO(0, false, true);
+                case 2: return NAQS_KO(0, true, false);
+                case 3: return NAQS_KO(0, true, true);
+                case 4: return NAQS_KO(1, false, false);
+                case 5: return NAQS_KO(1, false, true);
+                case 6: return NAQS_KO(1, true, false);
+                case 7: return NAQS_KO(1, true, true);
+                case 8: return NAQS_KO(2, false, false);
+                case 9: return NAQS_KO(2, false, true);
+                case 10: return NAQS_KO(2, true, false);
+                default: return NAQS_KO(2, true, true);
             }
 #undef NAQS_KO
         }
@@ -565,7 +597,7 @@ int naqs_apply_h(naqs_table_t* t, const uint64_t* d_states, int64_t M, double* d
 }
 
 int naqs_eloc_host(naqs_table_t* t, const uint64_t* h_states, const void* h_psi, int psi_dtype, int64_t M,
-                   const uint64_t* h_tkeys, const void* h_tpsi, int64_t T, double* h_eloc) {
+                   const uint64_t* h_tkeys, const void* h_tpsi, int64_t T, int lookup_kind, double* h_eloc) {
     NAQS_REQUIRE(t, NAQS_ERR_ARG, "naqs_eloc_host: NULL table");
     NAQS_REQUIRE(M >= 0 && (M == 0 || (h_states && h_psi && h_eloc)), NAQS_ERR_ARG, "naqs_eloc_host: NULL buffers");
     NAQS_REQUIRE(psi_dtype == NAQS_C128 || psi_dtype == NAQS_C64, NAQS_ERR_DTYPE, "naqs_eloc_host: psi must be complex64 or complex128");
@@ -594,7 +626,7 @@ int naqs_eloc_host(naqs_table_t* t, const uint64_t* h_states, const void* h_psi,
         NAQS_CUDA(cudaMemcpyAsync(d + o_tp, h_tpsi, T * psz, cudaMemcpyHostToDevice, st));
         d_tk = (const uint64_t*)(d + o_tk); d_tp = d + o_tp;
     }
-    int rc = naqs_lookup_build(t, d_tk, d_tp, psi_dtype, T, NAQS_LOOKUP_AUTO, st);
+    int rc = naqs_lookup_build(t, d_tk, d_tp, psi_dtype, T, lookup_kind, st);
     if (rc) return rc;
     rc = naqs_eloc(t, (const uint64_t*)(d + o_states), d + o_psi, psi_dtype, M, (double*)(d + o_out), st);
     if (rc) return rc;

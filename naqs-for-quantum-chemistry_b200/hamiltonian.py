@@ -85,10 +85,12 @@ class PauliHamiltonianB200:
                   f"(device {self.table.device}).")
 
     # ------------------------------------------------------------------ fused path
-    def local_energy(self, states_idx, psi, ret_numpy=True):
+    def local_energy(self, states_idx, psi, ret_numpy=True, assume_unique=True):
         """E_loc (complex128) of the sampled batch, only couplings inside the batch contribute
-        (energy.py:247-248).  Stateless: nothing is cached."""
-        out = self.table.local_energy(np.asarray(states_idx).reshape(-1) if not torch.is_tensor(states_idx) else states_idx.reshape(-1), psi)
+        (energy.py:247-248).  Stateless: nothing is cached.  assume_unique=True as in the reference's call
+        update_H(states_idx, check_unseen=True, assume_unique=True) (energy.py:245)."""
+        out = self.table.local_energy(np.asarray(states_idx).reshape(-1) if not torch.is_tensor(states_idx) else states_idx.reshape(-1), psi,
+                                      assume_unique=assume_unique)
         return _lib.complex_from_pairs(out) if ret_numpy else out
 
     def linear_operator(self, states_idx):

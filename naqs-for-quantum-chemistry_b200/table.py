@@ -63,20 +63,24 @@ class DeviceTermTable:
         return _lib.stream_ptr(self.device)
 
     # ------------------------------------------------------------------ amplitude lookup
-    def build_lookup(self, keys, psi, kind=LOOKUP_AUTO):
-        """(key, psi) pairs of the sampled batch -> device lookup structure (duplicates summed)."""
+    def build_lookup(self, keys, psi, kind=LOOKUP_AUTO, assume_unique=False):
+        """(key, psi) pairs of the sampled batch -> device lookup structure (duplicates summed).
+        assume_unique=True is the reference's own contract at the call site (energy.py:245 passes assume_unique=True): it
+        lets the dense table keep complex64 amplitudes as 8-byte entries."""
         k = self._keys(keys)
         p, code = _lib.psi_to_device(psi, self.device)
         if p.shape[0] != k.shape[0]:
             raise ValueError("keys and psi must have the same length")
         with torch.cuda.device(self.device):
-            _lib.check(_lib.load().naqs_lookup_build(self._h, _lib.ptr(k), _lib.ptr(p), code, k.shape[0], kind, self._stream()),
+            _lib.check(_lib.load().naqs_lookup_build(self._h, _lib.ptr(k), _lib.ptr(p), code, k.shape[0],
+                                                     kind | (_lib.LOOKUP_ASSUME_UNIQUE if assume_unique else 0), self._stream()),
                        "naqs_lookup_build")
         self._lookup_built = True
         return self
 
     # ------------------------------------------------------------------ fused E_loc (Level-1)
-    def local_energy(self, states, psi, table_keys=None, table_psi=None, kind=LOOKUP_AUTO, out=None, rebuild_lookup=True):
+    def local_energy(self, states, psi, table_keys=None, table_psi=None, kind=LOOKUP_AUTO, out=None, rebuild_lookup=True,
+                     assume_unique=False):
         """E_loc of every state in `states` (src/optimizer/energy.py:245-248), complex128.
 
         states/psi on the host (numpy / CPU tensors) or on the device (CUDA tensors).  The lookup table is
@@ -89,9 +93,9 @@ class DeviceTermTable:
             raise ValueError("states and psi must have the same length")
         if rebuild_lookup or not self._lookup_built:
             if table_keys is None:
-                self.build_lookup(k, torch.view_as_complex(p), kind)
+                self.build_lookup(k, torch.view_as_complex(p), kind, assume_unique)
             else:
-                self.build_lookup(table_keys, table_psi, kind)
+                self.build_lookup(table_keys, table_psi, kind, assume_unique)
         if out is None:
             out = torch.empty((M, 2), dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
@@ -109,7 +113,7 @@ class DeviceTermTable:
             _lib.check(_lib.load().naqs_apply_h(self._h, _lib.ptr(k), k.shape[0], _lib.ptr(out), self._stream()), "naqs_apply_h")
         return out
 
-    def local_energy_host(self, states, psi, table_keys=None, table_psi=None, out=None):
+    def local_energy_host(self, states, psi, table_keys=None, table_psi=None, out=None, kind=LOOKUP_AUTO, assume_unique=False):
         """Host-buffer path (numpy in, numpy complex128 out) through naqs_eloc_host: upload -> lookup build -> fused
         kernel -> download, synchronous.  Page-locked inputs / `out` (e.g. numpy views of pinned torch tensors) make the
         copies run at full PCIe rate; pageable arrays work too, only slower."""
@@ -129,7 +133,7 @@ class DeviceTermTable:
             tp = np.ascontiguousarray(table_psi).astype(p.dtype)
             T = len(tk)
         _lib.check(_lib.load().naqs_eloc_host(self._h, _lib.ptr(k), _lib.ptr(p), code, len(k), _lib.ptr(tk), _lib.ptr(tp), T,
-                                              _lib.ptr(out)), "naqs_eloc_host")
+                                              kind | (_lib.LOOKUP_ASSUME_UNIQUE if assume_unique else 0), _lib.ptr(out)), "naqs_eloc_host")
         return out
 
     # ------------------------------------------------------------------ stored rows (CSR / coupled sets)

@@ -74,6 +74,10 @@ def test_eloc_matches_reference_fixture(name):
     assert np.array_equal(gpu_eloc(t, case["states"], case["psi"].astype(np.complex128)), e)
     # host-buffer entry (naqs_eloc_host) == device-buffer entry
     assert np.array_equal(t.local_energy_host(case["states"], case["psi"]), e)
+    # assume_unique (the reference's own call-site contract, energy.py:245) may switch to the complex64 dense table
+    e_u = gpu_eloc(t, case["states"], case["psi"], assume_unique=True)
+    assert rel_err(e_u, case["eloc"]).max() <= ELOC_RTOL and rel_err(e_u, e).max() <= 1e-13
+    assert np.array_equal(t.local_energy_host(case["states"], case["psi"], assume_unique=True), e_u)
 
 
 @pytest.mark.parametrize("name", ["LiH_sector", "LiH_small", "H2O_sector", "LiH_full_600"])
@@ -406,6 +410,9 @@ def test_full_size_properties_n2_1e6():
     sub = rng.choice(len(st), 3000, replace=False)
     ref = ct.local_energy(st[sub], psi[sub], st, psi)
     assert rel_err(e[sub], ref).max() <= ELOC_RTOL
+    # (4b) unique-key contract -> complex64 dense table: same numbers to rounding, still within 1e-12 of the oracle
+    e_u = gpu_eloc(t, st, psi, assume_unique=True)
+    assert rel_err(e_u[sub], ref).max() <= ELOC_RTOL and rel_err(e_u, e).max() <= 1e-13
     # (5) hash lookup (row-order walk) == dense lookup (key-order walk) at full size
     assert rel_err(gpu_eloc(t, st, psi, kind=nb200._lib.LOOKUP_HASH), e).max() <= 1e-13
 
