@@ -114,31 +114,34 @@ struct LookupView {
     const float2* dense32;   // [2^N] complex64 copy of the dense table (unique keys + complex64 psi only) or nullptr
 };
 
-// Bloom filter of the hash lookup: 2^19 bits = 64 KB, copied into shared memory by every CTA of the 1024-thread launch
-// shape.  In a sparse VMC batch almost every coupled state is NOT in the table; the filter answers those with two
-// shared-memory reads instead of a global sector read.  Built only while it has >= 4 bits per key.
-constexpr uint32_t kFilterBits = 1u << 19;
-constexpr uint32_t kFilterBytes = kFilterBits / 8;
-__host__ __device__ inline void filter_positions(uint32_t h, uint32_t& b1, uint32_t& b2) {
-    b1 = h & (kFilterBits - 1);
-    b2 = (h * 0x9E3779B1u) >> (32 - 19);
-}
+
 
 __host__ __device__ inline unsigned long long mix64(unsigned long long x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
     return x;
 }
-// 32-bit multiplicative hash of a (up to 128-bit) key, a handful of IMAD/SHF/LOP3: the probe sequence starts at
-// hash32 >> shift.  Table capacities are powers of two <= 2^31 with load factor <= 0.5.
+// Multiplicative (Fibonacci) hashing: the top bits of key * odd-constant depend on every key bit.  Two independent
+// products give the bucket index / first filter position and the second filter position — 2 IMAD + 3 SHF per key of
+// <= 32 bits.  Table capacities are powers of two <= 2^31.
 __host__ __device__ inline uint32_t hash32(unsigned long long k0, unsigned long long k1) {
-    uint32_t h = (uint32_t)k0 * 0x9E3779B1u + (uint32_t)(k0 >> 32) * 0x85EBCA6Bu + (uint32_t)k1 * 0xC2B2AE35u +
-                 (uint32_t)(k1 >> 32) * 0x27D4EB2Fu;
-    h = (h ^ (h >> 15)) * 0x2C1B3C6Du;
-    h ^= h >> 13;
-    return h * 0x297A2D39u;
+    return (uint32_t)k0 * 0x9E3779B1u + (uint32_t)(k0 >> 32) * 0x85EBCA6Bu + (uint32_t)k1 * 0xC2B2AE35u +
+           (uint32_t)(k1 >> 32) * 0x27D4EB2Fu;
+}
+__host__ __device__ inline uint32_t hash32b(unsigned long long k0) {
+    return (uint32_t)k0 * 0x7FEB352Du + (uint32_t)(k0 >> 32) * 0x846CA68Bu;
 }
 __host__ __device__ inline unsigned long long hash_slot(unsigned long long k0, unsigned long long k1, int shift) {
     return (unsigned long long)(hash32(k0, k1) >> shift);
+}
+
+// Bloom filter of the hash lookup: 2^19 bits = 64 KB, copied into shared memory by every CTA of the 1024-thread launch
+// shape.  In a sparse VMC batch almost every coupled state is NOT in the table; the filter answers those with two
+// shared-memory reads instead of a global sector read.  Built only while it has >= 4 bits per key.
+constexpr uint32_t kFilterBits = 1u << 19;
+constexpr uint32_t kFilterBytes = kFilterBits / 8;
+__host__ __device__ inline void filter_positions(unsigned long long k0, uint32_t h, uint32_t& b1, uint32_t& b2) {
+    b1 = h >> (32 - 19);
+    b2 = hash32b(k0) >> (32 - 19);
 }
 
 }  // namespace naqs

@@ -298,15 +298,15 @@ __device__ __forceinline__ void heavy_lookup(int n, const double (&h)[B], const 
         uint32_t j[NW];
 #pragma unroll
         for (int w = 0; w < NW; ++w) j[w] = on[b] ? (s[w] ^ u[b][w]) : s[w];
-        if constexpr (SEC) on[b] = on[b] && in_sector<NW>(j, sec);
+        if constexpr (SEC) on[b] = on[b] & in_sector<NW>(j, sec);
         key_words64<NW>(j, k0[b], k1[b]);
         if constexpr (NW <= 2) {
             const uint32_t hh = hash32(k0[b], 0ull);
             slot[b] = hh >> lv.bshift;
             if (sfilt) {  // a clear bit proves the key is not in the table: no global access at all
                 uint32_t b1, b2;
-                filter_positions(hh, b1, b2);
-                on[b] = on[b] && ((sfilt[b1 >> 5] >> (b1 & 31)) & (sfilt[b2 >> 5] >> (b2 & 31)) & 1u);
+                filter_positions(k0[b], hh, b1, b2);
+                on[b] = on[b] & (((sfilt[b1 >> 5] >> (b1 & 31)) & (sfilt[b2 >> 5] >> (b2 & 31)) & 1u) != 0);
             }
         } else {
             slot[b] = (unsigned)hash_slot(k0[b], k1[b], lv.shift);
@@ -432,19 +432,18 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
         constexpr uint32_t QSTRIDE = THREADS * 4;  // bytes between consecutive queue slots of one thread
         unsigned char* const q0 = smem + queue_offset + threadIdx.x * 4;
         unsigned char* qtail = q0;            // the queue holds (qtail - q0) / QSTRIDE couplings
-        constexpr int PB = 4;  // couplings resolved per thread and round
+        constexpr int PB = 2;  // couplings resolved per thread and round
         auto pop_round = [&](const unsigned char* __restrict__ buf) {
             const int n = min((int)((uint32_t)(qtail - q0) / QSTRIDE), PB);
             double h[PB];
             const uint32_t* u[PB];
 #pragma unroll
             for (int b = 0; b < PB; ++b) {
-                h[b] = 0.0; u[b] = reinterpret_cast<const uint32_t*>(buf);
-                if (b < n) {
-                    const uint32_t e = *reinterpret_cast<const uint32_t*>(qtail - (b + 1) * QSTRIDE);
-                    h[b] = *reinterpret_cast<const double*>(buf + (e & 0xffffu) * 8u);
-                    u[b] = reinterpret_cast<const uint32_t*>(buf + (e >> 16) * 4u);
-                }
+                // always read a valid slot (the oldest one when the queue is shorter than b + 1): no branch, lanes are masked by n
+                const unsigned char* slot = b < n ? qtail - (b + 1) * QSTRIDE : q0;
+                const uint32_t e = *reinterpret_cast<const uint32_t*>(slot);
+                h[b] = *reinterpret_cast<const double*>(buf + (e & 0xffffu) * 8u);
+                u[b] = reinterpret_cast<const uint32_t*>(buf + (e >> 16) * 4u);
             }
             qtail -= n * QSTRIDE;
             heavy_lookup<NW, SEC, PB>(n, h, u, s, sec, lv, sfilt, e_re, e_im);

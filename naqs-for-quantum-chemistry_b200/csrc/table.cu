@@ -100,7 +100,7 @@ __global__ void filter_build_kernel(uint32_t* filter, const uint64_t* __restrict
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t b1, b2;
-    filter_positions(hash32(keys[i * words], 0ull), b1, b2);
+    filter_positions(keys[i * words], hash32(keys[i * words], 0ull), b1, b2);
     atomicOr(&filter[b1 >> 5], 1u << (b1 & 31));
     atomicOr(&filter[b2 >> 5], 1u << (b2 & 31));
 }
