@@ -351,14 +351,23 @@ def main():
     if not args.no_e2e:
         def e2e_step():
             if world == 1 and not dedup:
-                return table.local_energy_host(h_states_np, h_psi_np, out=h_eloc_np, assume_unique=True)
+                return table.local_energy_host(h_keys_np, h_psi_np, out=h_eloc32_np, assume_unique=True, out_dtype=np.complex64)
             ds, dp = h_states.to(dev, non_blocking=True), h_psi.to(dev, non_blocking=True)
             step(ds, dp, d_eloc)
             h_eloc.copy_(d_eloc, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return h_eloc
-        h_states_np, h_psi_np = h_states.numpy().view(np.uint64), h_psi.numpy()       # views of the pinned buffers
-        h_eloc_np = torch.view_as_complex(h_eloc).numpy()
+        # the reference-facing call: state indices in the reference's index dtype (int32 for 16 <= N < 30, hilbert.py:405-410),
+        # psi complex64, E_loc back as float32 pairs (complex.py:139-140); all three buffers page-locked
+        idt = torch.int16 if wl["N"] < 16 else (torch.int32 if wl["N"] < 30 else torch.int64)
+        if W == 1:
+            h_keys = h_states.reshape(-1).to(idt).pin_memory()
+            h_keys_np = h_keys.numpy() if idt != torch.int64 else h_keys.numpy().view(np.uint64)
+        else:
+            h_keys_np = h_states.numpy().view(np.uint64)
+        h_psi_np = h_psi.numpy()
+        h_eloc32 = torch.empty(M, dtype=torch.complex64).pin_memory()
+        h_eloc32_np = h_eloc32.numpy()
         for _ in range(3):
             e2e_step()
         barrier()
@@ -370,10 +379,13 @@ def main():
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * M * K * n_e2e / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(M * (8 * W + 8)),
-               "d2h_bytes_per_step": int(M * 16), "steps": n_e2e,
-               "api": "DeviceTermTable.local_energy_host -> naqs_eloc_host (host numpy in, complex128 E_loc out)" if world == 1 and not dedup
-                      else "pinned H2D + step + pinned D2H of E_loc"}
+        host_api = world == 1 and not dedup
+        e2e = {"value": world * M * K * n_e2e / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(M * (h_keys_np.itemsize * (1 if W == 1 else W) + 8)) if host_api else int(M * (8 * W + 8)),
+               "d2h_bytes_per_step": int(M * 8) if host_api else int(M * 16), "steps": n_e2e,
+               "api": "DeviceTermTable.local_energy_host -> naqs_eloc_host: pinned host state indices (reference index dtype) + complex64 psi in, "
+                      "E_loc out as float32 pairs (what calculate_local_energy returns, complex.py:139-140); complex128 arithmetic" if host_api
+                      else "pinned H2D of keys + psi, multi-GPU step, pinned D2H of complex128 E_loc"}
 
     if rank != 0:
         if world > 1:

@@ -108,13 +108,18 @@ int naqs_apply_h(naqs_table_t* t, const uint64_t* d_states, int64_t n_states, do
  * Both give bit-identical H_ij.  The environment variable NAQS_ELOC_ALGO=direct sets the default. */
 int naqs_table_set_algo(naqs_table_t* t, int algo);
 
-/* Same through HOST buffers (what a caller holding numpy arrays uses; bench.py's e2e leg): uploads
- * states + psi, builds the lookup table from the same (states, psi) batch, runs naqs_eloc and
- * downloads E_loc.  Synchronous.  h_table_keys may be NULL (=> the batch is its own table, the
- * reference's only mode) or T separate (key, psi) pairs. */
-int naqs_eloc_host(naqs_table_t* t, const uint64_t* h_states, const void* h_psi, int psi_dtype, int64_t n_states,
-                   const uint64_t* h_table_keys, const void* h_table_psi, int64_t n_table,
-                   int lookup_kind /* NAQS_LOOKUP_* [| NAQS_LOOKUP_ASSUME_UNIQUE] */, double* h_eloc);
+/* Same through HOST buffers (what a caller holding numpy arrays / CPU tensors uses; bench.py's e2e leg): uploads
+ * states + psi, builds the lookup table, runs naqs_eloc and downloads E_loc.  Synchronous.
+ *   key_itemsize : 8 = `words` uint64 per key; 4 / 2 = the reference's int32 / int16 state indices
+ *                  (src/utils/hilbert.py:405-410), single-word keys only
+ *   h_table_keys : NULL => the batch is its own lookup table (the reference's only mode), else n_table (key, psi) pairs
+ *   lookup_kind  : NAQS_LOOKUP_* [| NAQS_LOOKUP_ASSUME_UNIQUE]
+ *   eloc_dtype   : NAQS_C128, or NAQS_C64 = the float32 pairs the reference returns to torch (src/utils/complex.py:139-140);
+ *                  the arithmetic is complex128 either way.
+ * Page-locked host buffers make the copies run at full PCIe rate; pageable ones work too. */
+int naqs_eloc_host(naqs_table_t* t, const void* h_states, int key_itemsize, const void* h_psi, int psi_dtype, int64_t n_states,
+                   const void* h_table_keys, const void* h_table_psi, int64_t n_table, int lookup_kind,
+                   void* h_eloc, int eloc_dtype);
 
 /* ------------------------------------------------------------------------------------------
  * Stored Hamiltonian rows (CSR / coupled-set mode) — replaces update_H's row construction

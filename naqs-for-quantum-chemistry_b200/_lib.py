@@ -31,7 +31,7 @@ SIGNATURES = {
     "naqs_eloc": (_i, [_p, _p, _p, _i, _i64, _p, _p]),
     "naqs_table_set_algo": (_i, [_p, _i]),
     "naqs_apply_h": (_i, [_p, _p, _i64, _p, _p]),
-    "naqs_eloc_host": (_i, [_p, _p, _p, _i, _i64, _p, _p, _i64, _i, _p]),
+    "naqs_eloc_host": (_i, [_p, _p, _i, _p, _i, _i64, _p, _p, _i64, _i, _p, _i]),
     "naqs_rows_count": (_i, [_p, _p, _i64, _p, _p]),
     "naqs_exclusive_scan": (_i, [_p, _p, _i64, _p, _p]),
     "naqs_rows_fill": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p]),

@@ -105,6 +105,17 @@ __global__ void filter_build_kernel(uint32_t* filter, const uint64_t* __restrict
     atomicOr(&filter[b2 >> 5], 1u << (b2 & 31));
 }
 
+__global__ void widen_keys_kernel(const void* __restrict__ in, int itemsize, int64_t n, uint64_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = itemsize == 4 ? (uint64_t)reinterpret_cast<const uint32_t*>(in)[i] : (uint64_t)reinterpret_cast<const uint16_t*>(in)[i];
+}
+
+__global__ void narrow_eloc_kernel(const double2* __restrict__ in, int64_t n, float2* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_float2((float)in[i].x, (float)in[i].y);
+}
+
 __global__ void dense_scatter32_kernel(float2* dense, const uint64_t* __restrict__ keys, const float2* __restrict__ psi, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dense[keys[i]] = psi[i];  // unique keys (caller's guarantee): a plain store
@@ -596,20 +607,25 @@ int naqs_apply_h(naqs_table_t* t, const uint64_t* d_states, int64_t M, double* d
     }
 }
 
-int naqs_eloc_host(naqs_table_t* t, const uint64_t* h_states, const void* h_psi, int psi_dtype, int64_t M,
-                   const uint64_t* h_tkeys, const void* h_tpsi, int64_t T, int lookup_kind, double* h_eloc) {
+int naqs_eloc_host(naqs_table_t* t, const void* h_states, int key_itemsize, const void* h_psi, int psi_dtype, int64_t M,
+                   const void* h_tkeys, const void* h_tpsi, int64_t T, int lookup_kind, void* h_eloc, int eloc_dtype) {
     NAQS_REQUIRE(t, NAQS_ERR_ARG, "naqs_eloc_host: NULL table");
     NAQS_REQUIRE(M >= 0 && (M == 0 || (h_states && h_psi && h_eloc)), NAQS_ERR_ARG, "naqs_eloc_host: NULL buffers");
     NAQS_REQUIRE(psi_dtype == NAQS_C128 || psi_dtype == NAQS_C64, NAQS_ERR_DTYPE, "naqs_eloc_host: psi must be complex64 or complex128");
+    NAQS_REQUIRE(eloc_dtype == NAQS_C128 || eloc_dtype == NAQS_C64, NAQS_ERR_DTYPE, "naqs_eloc_host: E_loc must be complex64 or complex128");
+    NAQS_REQUIRE(key_itemsize == 8 || ((key_itemsize == 4 || key_itemsize == 2) && t->words == 1), NAQS_ERR_DTYPE,
+                 "naqs_eloc_host: keys must be 64-bit words, or int16/int32 indices for single-word keys (hilbert.py:405-410)");
     if (M == 0) return NAQS_OK;
     DeviceGuard guard(t->device);
     const size_t psz = psi_dtype == NAQS_C64 ? 8 : 16;
-    const size_t kb = (size_t)8 * t->words;
+    const size_t kb_in = key_itemsize == 8 ? (size_t)8 * t->words : (size_t)key_itemsize, kb = (size_t)8 * t->words;
     const bool own_table = h_tkeys != nullptr;
     if (!own_table) T = M;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t o_states = 0, o_psi = al(M * kb), o_tk = o_psi + al(M * psz), o_tp = o_tk + (own_table ? al(T * kb) : 0),
-                 o_out = o_tp + (own_table ? al(T * psz) : 0), total = o_out + al((size_t)M * 16);
+    // staging layout: raw keys | keys64 | psi | [table raw keys | table keys64 | table psi] | eloc128 | eloc64
+    const size_t o_kraw = 0, o_k64 = al(M * kb_in), o_psi = o_k64 + al(M * kb), o_tkraw = o_psi + al(M * psz),
+                 o_tk64 = o_tkraw + (own_table ? al(T * kb_in) : 0), o_tp = o_tk64 + (own_table ? al(T * kb) : 0),
+                 o_out = o_tp + (own_table ? al(T * psz) : 0), o_out32 = o_out + al((size_t)M * 16), total = o_out32 + al((size_t)M * 8);
     if (t->stage_bytes < total) {
         cudaFree(t->d_stage); t->d_stage = nullptr; t->stage_bytes = 0;
         NAQS_CUDA(cudaMalloc(&t->d_stage, total));
@@ -617,20 +633,40 @@ int naqs_eloc_host(naqs_table_t* t, const uint64_t* h_states, const void* h_psi,
     }
     char* d = (char*)t->d_stage;
     cudaStream_t st = t->own_stream;
-    NAQS_CUDA(cudaMemcpyAsync(d + o_states, h_states, M * kb, cudaMemcpyHostToDevice, st));
+    auto upload_keys = [&](const void* h, size_t o_raw, size_t o_64, int64_t n, const uint64_t** out) -> int {
+        if (key_itemsize == 8) {
+            NAQS_CUDA(cudaMemcpyAsync(d + o_64, h, n * kb, cudaMemcpyHostToDevice, st));
+        } else {
+            NAQS_CUDA(cudaMemcpyAsync(d + o_raw, h, n * kb_in, cudaMemcpyHostToDevice, st));
+            widen_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d + o_raw, key_itemsize, n, (uint64_t*)(d + o_64));
+            NAQS_LAUNCHED();
+        }
+        *out = (const uint64_t*)(d + o_64);
+        return NAQS_OK;
+    };
+    const uint64_t *d_keys = nullptr, *d_tk = nullptr;
+    int rc = upload_keys(h_states, o_kraw, o_k64, M, &d_keys);
+    if (rc) return rc;
     NAQS_CUDA(cudaMemcpyAsync(d + o_psi, h_psi, M * psz, cudaMemcpyHostToDevice, st));
-    const uint64_t* d_tk = (const uint64_t*)(d + o_states);
     const void* d_tp = d + o_psi;
+    d_tk = d_keys;
     if (own_table) {
-        NAQS_CUDA(cudaMemcpyAsync(d + o_tk, h_tkeys, T * kb, cudaMemcpyHostToDevice, st));
+        rc = upload_keys(h_tkeys, o_tkraw, o_tk64, T, &d_tk);
+        if (rc) return rc;
         NAQS_CUDA(cudaMemcpyAsync(d + o_tp, h_tpsi, T * psz, cudaMemcpyHostToDevice, st));
-        d_tk = (const uint64_t*)(d + o_tk); d_tp = d + o_tp;
+        d_tp = d + o_tp;
     }
-    int rc = naqs_lookup_build(t, d_tk, d_tp, psi_dtype, T, lookup_kind, st);
+    rc = naqs_lookup_build(t, d_tk, d_tp, psi_dtype, T, lookup_kind, st);
     if (rc) return rc;
-    rc = naqs_eloc(t, (const uint64_t*)(d + o_states), d + o_psi, psi_dtype, M, (double*)(d + o_out), st);
+    rc = naqs_eloc(t, d_keys, d + o_psi, psi_dtype, M, (double*)(d + o_out), st);
     if (rc) return rc;
-    NAQS_CUDA(cudaMemcpyAsync(h_eloc, d + o_out, (size_t)M * 16, cudaMemcpyDeviceToHost, st));
+    if (eloc_dtype == NAQS_C64) {  // the reference hands E_loc to torch as float32 pairs (src/utils/complex.py:139-140)
+        narrow_eloc_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>((const double2*)(d + o_out), M, (float2*)(d + o_out32));
+        NAQS_LAUNCHED();
+        NAQS_CUDA(cudaMemcpyAsync(h_eloc, d + o_out32, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+    } else {
+        NAQS_CUDA(cudaMemcpyAsync(h_eloc, d + o_out, (size_t)M * 16, cudaMemcpyDeviceToHost, st));
+    }
     NAQS_CUDA(cudaStreamSynchronize(st));
     return NAQS_OK;
 }

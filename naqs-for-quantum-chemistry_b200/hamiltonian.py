@@ -89,6 +89,12 @@ class PauliHamiltonianB200:
         """E_loc (complex128) of the sampled batch, only couplings inside the batch contribute
         (energy.py:247-248).  Stateless: nothing is cached.  assume_unique=True as in the reference's call
         update_H(states_idx, check_unseen=True, assume_unique=True) (energy.py:245)."""
+        on_device = (torch.is_tensor(states_idx) and states_idx.is_cuda) or (torch.is_tensor(psi) and psi.is_cuda)
+        if ret_numpy and not on_device:
+            # host-resident batch (the reference's situation: sampler output is moved to the CPU, nade.py:727-733):
+            # one C-ABI call that uploads, computes and downloads (naqs_eloc_host)
+            idx = states_idx.detach().numpy() if torch.is_tensor(states_idx) else np.asarray(states_idx)
+            return self.table.local_energy_host(np.ascontiguousarray(idx.reshape(-1)), psi, assume_unique=assume_unique)
         out = self.table.local_energy(np.asarray(states_idx).reshape(-1) if not torch.is_tensor(states_idx) else states_idx.reshape(-1), psi,
                                       assume_unique=assume_unique)
         return _lib.complex_from_pairs(out) if ret_numpy else out

@@ -113,27 +113,47 @@ class DeviceTermTable:
             _lib.check(_lib.load().naqs_apply_h(self._h, _lib.ptr(k), k.shape[0], _lib.ptr(out), self._stream()), "naqs_apply_h")
         return out
 
-    def local_energy_host(self, states, psi, table_keys=None, table_psi=None, out=None, kind=LOOKUP_AUTO, assume_unique=False):
-        """Host-buffer path (numpy in, numpy complex128 out) through naqs_eloc_host: upload -> lookup build -> fused
-        kernel -> download, synchronous.  Page-locked inputs / `out` (e.g. numpy views of pinned torch tensors) make the
-        copies run at full PCIe rate; pageable arrays work too, only slower."""
-        k = _lib.keys_to_numpy(states, self.words)
-        p = np.ascontiguousarray(psi)
+    def _host_keys(self, x):
+        """-> (contiguous numpy array, itemsize code) without copying when the caller already holds int16/int32/uint64 keys."""
+        if torch.is_tensor(x):
+            x = x.detach().cpu().numpy()
+        a = np.asarray(x)
+        if self.words == 1 and a.dtype in (np.int16, np.uint16, np.int32, np.uint32) and a.flags.c_contiguous:
+            return a.reshape(-1), a.dtype.itemsize
+        return _lib.keys_to_numpy(a, self.words), 8
+
+    def local_energy_host(self, states, psi, table_keys=None, table_psi=None, out=None, kind=LOOKUP_AUTO, assume_unique=False,
+                          out_dtype=np.complex128):
+        """Host-buffer path (numpy / CPU tensors in, numpy out) through naqs_eloc_host: upload -> lookup build -> fused
+        kernel -> download, synchronous.  Keys may be the reference's int16 / int32 state indices or uint64 words; psi
+        complex64 / complex128; out_dtype complex128, or complex64 = the float32 pairs the reference returns to torch.
+        Page-locked inputs / `out` (e.g. numpy views of pinned torch tensors) make the copies run at full PCIe rate."""
+        k, ksz = self._host_keys(states)
+        n = len(k)
+        if torch.is_tensor(psi):
+            psi = (torch.view_as_complex(psi.detach().contiguous()) if not psi.is_complex() else psi.detach()).numpy()
+        p = np.ascontiguousarray(psi).reshape(-1)
         if p.dtype not in (np.complex64, np.complex128):
             p = p.astype(np.complex128)
         code = _lib.NAQS_C64 if p.dtype == np.complex64 else _lib.NAQS_C128
+        out_dtype = np.dtype(out_dtype)
+        if out_dtype not in (np.dtype(np.complex64), np.dtype(np.complex128)):
+            raise TypeError("out_dtype must be complex64 or complex128")
         if out is None:
-            out = np.empty(len(k), np.complex128)
-        elif out.dtype != np.complex128 or out.shape != (len(k),) or not out.flags.c_contiguous:
-            raise ValueError("out must be a contiguous complex128 array with one entry per state")
+            out = np.empty(n, out_dtype)
+        elif out.dtype != out_dtype or out.shape != (n,) or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous array of out_dtype with one entry per state")
         tk = tp = None
         T = 0
         if table_keys is not None:
-            tk = _lib.keys_to_numpy(table_keys, self.words)
-            tp = np.ascontiguousarray(table_psi).astype(p.dtype)
+            tk, tksz = self._host_keys(table_keys)
+            if tksz != ksz:
+                tk, k, ksz = _lib.keys_to_numpy(tk, self.words), _lib.keys_to_numpy(k, self.words), 8
+            tp = np.ascontiguousarray(table_psi).astype(p.dtype).reshape(-1)
             T = len(tk)
-        _lib.check(_lib.load().naqs_eloc_host(self._h, _lib.ptr(k), _lib.ptr(p), code, len(k), _lib.ptr(tk), _lib.ptr(tp), T,
-                                              kind | (_lib.LOOKUP_ASSUME_UNIQUE if assume_unique else 0), _lib.ptr(out)), "naqs_eloc_host")
+        _lib.check(_lib.load().naqs_eloc_host(self._h, _lib.ptr(k), ksz, _lib.ptr(p), code, n, _lib.ptr(tk), _lib.ptr(tp), T,
+                                              kind | (_lib.LOOKUP_ASSUME_UNIQUE if assume_unique else 0), _lib.ptr(out),
+                                              _lib.NAQS_C64 if out_dtype == np.dtype(np.complex64) else _lib.NAQS_C128), "naqs_eloc_host")
         return out
 
     # ------------------------------------------------------------------ stored rows (CSR / coupled sets)

@@ -78,6 +78,10 @@ def test_eloc_matches_reference_fixture(name):
     e_u = gpu_eloc(t, case["states"], case["psi"], assume_unique=True)
     assert rel_err(e_u, case["eloc"]).max() <= ELOC_RTOL and rel_err(e_u, e).max() <= 1e-13
     assert np.array_equal(t.local_energy_host(case["states"], case["psi"], assume_unique=True), e_u)
+    # the reference's index dtype (int16 / int32, hilbert.py:405-410) and float32-pair output (complex.py:139-140)
+    idt = np.int16 if N < 16 else np.int32
+    e32 = t.local_energy_host(case["states"].astype(np.int64).astype(idt), case["psi"], out_dtype=np.complex64)
+    assert e32.dtype == np.complex64 and np.array_equal(e32, e.astype(np.complex64))
 
 
 @pytest.mark.parametrize("name", ["LiH_sector", "LiH_small", "H2O_sector", "LiH_full_600"])
