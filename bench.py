@@ -41,6 +41,23 @@ def psi_for(n, seed):
     return (rng.normal(size=n) + 1j * rng.normal(size=n)).astype(np.complex64)
 
 
+def psi_of_keys(keys, n_qubits, seed=0):
+    """psi as a FUNCTION of the state (normal + 1j*normal, complex64, seeded): the same configuration gets the same amplitude
+    on every rank, as a wavefunction does.  For small spaces a 2^N table, otherwise a counter-based generator."""
+    keys = np.asarray(keys).reshape(-1)
+    if n_qubits <= 24:
+        rng = np.random.default_rng(seed)
+        full = (rng.normal(size=2 ** n_qubits) + 1j * rng.normal(size=2 ** n_qubits)).astype(np.complex64)
+        return full[keys.astype(np.int64)]
+    x = (keys.astype(np.uint64) + np.uint64(seed)) * np.uint64(0x9E3779B97F4A7C15)
+    x ^= x >> np.uint64(29); x *= np.uint64(0xBF58476D1CE4E5B9); x ^= x >> np.uint64(32)
+    u1 = ((x >> np.uint64(11)).astype(np.float64) + 0.5) / 2.0 ** 53
+    y = x * np.uint64(0x94D049BB133111EB); y ^= y >> np.uint64(31)
+    u2 = ((y >> np.uint64(11)).astype(np.float64) + 0.5) / 2.0 ** 53
+    r = np.sqrt(-2.0 * np.log(u1))
+    return (r * np.cos(2 * np.pi * u2) + 1j * r * np.sin(2 * np.pi * u2)).astype(np.complex64)
+
+
 def sector_states(N, na, nb, m, seed):
     rng = np.random.default_rng(seed)
     ev, od = np.arange(0, N, 2), np.arange(1, N, 2)
@@ -81,20 +98,20 @@ def make_workload(name, rank, m_override=None, synth=None):
         xy, yz, c, N, _, _ = load_table("N2")
         M = m_override or 1_000_000
         st = np.random.default_rng(rank).choice(2 ** N, M, replace=False).astype(np.uint64)
-        desc = f"N2 STO-3G (20 qubits, K=2239, Kxy=378), M={M} distinct keys of the unrestricted 2^20 space per GPU (seed=rank), sector filter off, psi complex64 (SURVEY.md §8d config 3)"
-        return dict(xy=xy, yz=yz, c=c, N=N, na=None, nb=None, states=st, psi=psi_for(M, rank), desc=desc, mol="N2")
+        desc = f"N2 STO-3G (20 qubits, K=2239, Kxy=378), M={M} distinct keys of the unrestricted 2^20 space per GPU (seed=rank), sector filter off, psi = seeded complex64 function of the key (SURVEY.md §8d config 3)"
+        return dict(xy=xy, yz=yz, c=c, N=N, na=None, nb=None, states=st, psi=psi_of_keys(st, N), desc=desc, mol="N2")
     if name == "h2o_1e5":
         xy, yz, c, N, _, _ = load_table("H2O")
         M = m_override or 100_000
         st = np.random.default_rng(rank).integers(0, 2 ** N, M).astype(np.uint64)
         desc = f"H2O STO-3G (14 qubits, K=1390), M={M} rows drawn with replacement from 2^14 (1e5 unique 14-qubit states do not exist), table = distinct keys (SURVEY.md §8d config 2)"
-        return dict(xy=xy, yz=yz, c=c, N=N, na=None, nb=None, states=st, psi=psi_for(M, rank), desc=desc, mol="H2O", dedup_table=True)
+        return dict(xy=xy, yz=yz, c=c, N=N, na=None, nb=None, states=st, psi=psi_of_keys(st, N), desc=desc, mol="H2O", dedup_table=True)
     if name == "li2o_1e5":
         xy, yz, c, N, na, nb = load_table("Li2O")
         M = m_override or 100_000
         st = sector_states(N, na, nb, M, rank)
         desc = f"Li2O STO-3G (30 qubits, K=20558, Kxy=3810), M={M} distinct (7,7)-sector states per GPU, sector filter on (SURVEY.md §8d config 4 batch)"
-        return dict(xy=xy, yz=yz, c=c, N=N, na=na, nb=nb, states=st, psi=psi_for(M, rank), desc=desc, mol="Li2O")
+        return dict(xy=xy, yz=yz, c=c, N=N, na=na, nb=nb, states=st, psi=psi_of_keys(st, N), desc=desc, mol="Li2O")
     if name == "synthetic":
         N, K, M = synth
         xy, yz, c = synthetic_table(N, K)
@@ -244,6 +261,74 @@ def cpu_baseline_sample(wl, sample, reps=2):
                       f"(reference Cython kernels from oracle/_ref + numpy/scipy orchestration of hamiltonian.py:272-370)"}
 
 
+def measure_extras(naqs_b200, dev, args):
+    """The other BASELINE.json configs on one GPU (device-resident couplings/s, same timing rules, fewer steps), and the
+    E_loc call of a LiH VMC iteration (config 0) through the reference-shaped host API next to the reference CPU path."""
+    import torch
+    out = {}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for name in ("h2o_1e5", "li2o_1e5"):
+        if name == args.workload:
+            continue
+        wl = make_workload(name, 0)
+        table = naqs_b200.DeviceTermTable(wl["xy"], wl["yz"], wl["c"], wl["N"], wl["na"], wl["nb"], device=dev)
+        M, K = len(wl["states"]), table.K
+        d_states = torch.from_numpy(np.ascontiguousarray(wl["states"]).reshape(M, -1).view(np.int64)).to(dev)
+        d_psi = torch.from_numpy(wl["psi"]).to(dev)
+        d_out = torch.empty((M, 2), dtype=torch.float64, device=dev)
+        if wl.get("dedup_table"):
+            uk, first = np.unique(wl["states"], return_index=True)
+            tk, tp = torch.from_numpy(uk.view(np.int64)).to(dev).reshape(-1, 1), d_psi[torch.from_numpy(first).to(dev)]
+        else:
+            tk, tp = d_states, d_psi
+        ms = []
+        for i in range(5 + 20):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            table.build_lookup(tk, tp, assume_unique=True)
+            table.local_energy(d_states, d_psi, out=d_out, rebuild_lookup=False)
+            table.stats(d_out)
+            e1.record()
+            e1.synchronize()
+            if i >= 5:
+                ms.append(e0.elapsed_time(e1))
+        out[name] = {"value": M * K * len(ms) / (sum(ms) * 1e-3), "unit": UNIT, "ms_per_step": sum(ms) / len(ms), "steps": len(ms),
+                     "workload": wl["desc"]}
+        del table
+    # config 0: the E_loc call inside a LiH VMC iteration (<= 225 unique states): latency of one call
+    xy, yz, c, N, na, nb = load_table("LiH")
+    case = np.load(os.path.join(GOLDEN, "eloc_LiH_sector.npz"))
+    st, psi = case["states"].astype(np.int64).astype(np.int16), case["psi"]
+    table = naqs_b200.DeviceTermTable(xy, yz, c, N, na, nb, device=dev)
+    for _ in range(5):
+        table.local_energy_host(st, psi, assume_unique=True, out_dtype=np.complex64)
+    t0 = time.perf_counter()
+    n = 200
+    for _ in range(n):
+        table.local_energy_host(st, psi, assume_unique=True, out_dtype=np.complex64)
+    b200_ms = 1e3 * (time.perf_counter() - t0) / n
+    lih = {"states": int(len(st)), "terms": int(len(c)), "b200_host_call_ms": b200_ms}
+    try:
+        from oracle import ref_path
+        path = ref_path.ReferencePath(xy, yz, c, N, na, nb)
+        cold = []
+        for _ in range(5):
+            path.reset()
+            t0 = time.perf_counter()
+            path.local_energy(st.astype(np.int64), psi)
+            cold.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            path.local_energy(st.astype(np.int64), psi)  # warm H cache: only get_H + sparse_dense_mv
+        warm = (time.perf_counter() - t0) / 20
+        lih.update({"reference_cpu_cold_cache_ms": 1e3 * min(cold), "reference_cpu_warm_cache_ms": 1e3 * warm, "cores": os.cpu_count()})
+    except Exception as e:  # noqa: BLE001
+        lih["reference_cpu"] = f"unavailable: {e}"
+    out["lih_vmc_eloc_call"] = lih
+    return out
+
+
 # ----------------------------------------------------------------------------------------- B200 arm
 def main():
     ap = argparse.ArgumentParser()
@@ -257,6 +342,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="states of the bounded cpu_baseline sample (0 = skip)")
     ap.add_argument("--ref-sample", type=int, default=50_000, help="states per step of --impl reference")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs and the LiH call-latency leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -302,7 +388,8 @@ def main():
         if world > 1:
             # public multi-GPU API: all-gather (key, psi) -> lookup build -> fused E_loc on the shard -> all-reduce of 5 sums
             g_k, g_p, _ = naqs_b200.distributed.gather_table(states, psi, equal_sizes=True, out=(g_states, g_psi))
-            table.build_lookup(g_k, g_p)  # gathered shards may share keys -> duplicates summed (complex128 table)
+            # ranks may have sampled the same configuration; psi is a function of the state, so one copy per key is kept
+            table.build_lookup(g_k, g_p, duplicates_equal=True)
         elif dedup:
             table.build_lookup(t_keys, t_psi, assume_unique=True)
         else:
@@ -419,6 +506,12 @@ def main():
                               "l1tex_data_pipe_pct_ncu": ncu["l1tex_data_pipe_pct"], "issue_active_pct_ncu": ncu["issue_active_pct"],
                               "frac": max(ncu["l1tex_data_pipe_pct"], ncu["issue_active_pct"]) / 100.0,
                               "ncu_source": ncu.get("source")})
+    extras = None
+    if world == 1 and not args.no_extras:
+        try:
+            extras = measure_extras(naqs_b200, dev, args)
+        except Exception as e:  # noqa: BLE001
+            extras = {"error": repr(e)}
     cpu = None
     if world == 1 and args.cpu_sample > 0:
         try:
@@ -432,7 +525,7 @@ def main():
                        "parallelism": f"states sharded x{world}, Pauli table replicated" + (", NCCL all-gather of (key, psi) + all-reduce of 5 fp64 sums" if world > 1 else ""),
                        "l2": "256 MB device memset between timed steps (L2 flush, untimed)", "timing": "CUDA events per step on the launching stream, max over ranks"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_pipe": roofline_pipe,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "other_configs": extras,
             "check": {"mean_eloc_re": float(stats[1] / stats[0]), "n": int(stats[4])}}
     print(json.dumps(line))
     if world > 1:

@@ -49,6 +49,10 @@ enum { NAQS_LOOKUP_AUTO = 0, NAQS_LOOKUP_DENSE = 1, NAQS_LOOKUP_HASH = 2 };
  * update_H(states_idx, check_unseen=True, assume_unique=True) (src/optimizer/energy.py:245).  Lets the dense lookup keep
  * complex64 amplitudes as 8-byte entries (no duplicate summation needed), halving the lines a table read touches. */
 #define NAQS_LOOKUP_ASSUME_UNIQUE 0x100
+/* OR-ed into `kind`: keys may repeat, but every copy of a key carries the SAME amplitude (psi is a function of the
+ * state; e.g. the all-gathered shards of several ranks that sampled the same configuration).  Copies are then dropped
+ * instead of summed — one amplitude per key — which also permits the 8-byte-entry dense table. */
+#define NAQS_LOOKUP_DUPLICATES_EQUAL 0x200
 
 typedef struct naqs_table naqs_table_t; /* opaque, device resident */
 

@@ -15,6 +15,7 @@ from . import _build
 NAQS_C128, NAQS_C64 = 0, 1
 LOOKUP_AUTO, LOOKUP_DENSE, LOOKUP_HASH = 0, 1, 2
 LOOKUP_ASSUME_UNIQUE = 0x100
+LOOKUP_DUPLICATES_EQUAL = 0x200
 _OK, _ERR_ARG, _ERR_DTYPE, _ERR_CUDA, _ERR_ALLOC, _ERR_STATE = range(6)
 
 # every symbol include/naqs_eloc.h declares: (restype, argtypes)

@@ -74,7 +74,7 @@ __global__ void bucket_init_kernel(HashBucket* buckets, int64_t n) {
 }
 
 __global__ void bucket_insert_kernel(HashBucket* buckets, unsigned bmask, int bshift, const uint64_t* __restrict__ keys, int words,
-                                     const void* __restrict__ psi, int psi_dtype, int64_t n) {
+                                     const void* __restrict__ psi, int psi_dtype, int64_t n, int keep_one) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long k = keys[i * words];
@@ -85,6 +85,10 @@ __global__ void bucket_insert_kernel(HashBucket* buckets, unsigned bmask, int bs
         for (int s = 0; s < 4; ++s) {
             const unsigned long long old = atomicCAS(&bk->key[s], kEmptyKey63, k);
             if (old == kEmptyKey63 || (old & kKeyMask63) == k) {
+                if (keep_one) {  // copies carry the same amplitude: the thread that claimed the slot stores it
+                    if (old == kEmptyKey63) bk->psi[s] = p;
+                    return;
+                }
                 // duplicates of a key are summed (scipy's H[idx[:,None], idx] repeats the column)
                 atomicAdd(&bk->psi[s].x, p.x);
                 atomicAdd(&bk->psi[s].y, p.y);
@@ -122,12 +126,13 @@ __global__ void dense_scatter32_kernel(float2* dense, const uint64_t* __restrict
 }
 
 __global__ void dense_scatter_kernel(double2* dense, const uint64_t* __restrict__ keys, const void* __restrict__ psi,
-                                     int psi_dtype, int64_t n) {
+                                     int psi_dtype, int64_t n, int overwrite) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double2 p = load_psi(psi, psi_dtype, i);
+    if (overwrite) { dense[keys[i]] = p; return; }  // copies of a key carry the same amplitude: keep one
     double* dst = reinterpret_cast<double*>(dense + keys[i]);
-    atomicAdd(dst, p.x);
+    atomicAdd(dst, p.x);  // duplicates of a key are summed (scipy's H[idx[:,None], idx] repeats the column)
     atomicAdd(dst + 1, p.y);
 }
 
@@ -312,7 +317,8 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
     NAQS_REQUIRE(psi_dtype == NAQS_C128 || psi_dtype == NAQS_C64, NAQS_ERR_DTYPE, "naqs_lookup_build: psi must be complex64 or complex128");
     DeviceGuard guard(t->device);
     cudaStream_t stream = (cudaStream_t)stream_;
-    const bool assume_unique = (kind & NAQS_LOOKUP_ASSUME_UNIQUE) != 0;
+    const bool dup_equal = (kind & NAQS_LOOKUP_DUPLICATES_EQUAL) != 0;
+    const bool assume_unique = (kind & NAQS_LOOKUP_ASSUME_UNIQUE) != 0 || dup_equal;  // plain stores are exact in both cases
     kind &= 0xff;
     if (kind == NAQS_LOOKUP_AUTO) kind = (t->n_qubits <= 22) ? NAQS_LOOKUP_DENSE : NAQS_LOOKUP_HASH;
     t->dense32_valid = false;
@@ -346,7 +352,7 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
         } else {
             NAQS_CUDA(cudaMemsetAsync(t->d_dense, 0, (size_t)entries * sizeof(double2), stream));
             if (n > 0) {
-                dense_scatter_kernel<<<blocks, 256, 0, stream>>>(t->d_dense, d_keys, d_psi, psi_dtype, n);
+                dense_scatter_kernel<<<blocks, 256, 0, stream>>>(t->d_dense, d_keys, d_psi, psi_dtype, n, dup_equal ? 1 : 0);
                 NAQS_LAUNCHED();
             }
         }
@@ -366,7 +372,7 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
         NAQS_LAUNCHED();
         if (n > 0) {
             const LookupView lv = t->lookup();
-            bucket_insert_kernel<<<blocks, 256, 0, stream>>>(t->d_buckets, lv.bmask, lv.bshift, d_keys, t->words, d_psi, psi_dtype, n);
+            bucket_insert_kernel<<<blocks, 256, 0, stream>>>(t->d_buckets, lv.bmask, lv.bshift, d_keys, t->words, d_psi, psi_dtype, n, dup_equal ? 1 : 0);
             NAQS_LAUNCHED();
         }
         t->filter_valid = false;

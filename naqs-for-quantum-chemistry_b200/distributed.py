@@ -78,7 +78,8 @@ def reduce_stats(sums5, group=None):
     return sums5
 
 
-def sharded_local_energy(table, keys_shard, psi_shard, weights_shard=None, group=None, out=None, equal_sizes=False, gather_out=None):
+def sharded_local_energy(table, keys_shard, psi_shard, weights_shard=None, group=None, out=None, equal_sizes=False, gather_out=None,
+                         duplicates_equal=False):
     """E_loc of this rank's shard against the batch of ALL ranks, plus the globally reduced statistics.
 
     table: DeviceTermTable (replicated on every rank); keys_shard / psi_shard: CUDA tensors (or host arrays) of the
@@ -89,7 +90,9 @@ def sharded_local_energy(table, keys_shard, psi_shard, weights_shard=None, group
     p, _ = _lib.psi_to_device(psi_shard, table.device)
     pc = torch.view_as_complex(p)
     g_keys, g_psi, _ = gather_table(k, pc, group, equal_sizes=equal_sizes, out=gather_out)
-    table.build_lookup(g_keys, g_psi)
+    # several ranks may have sampled the same configuration: by default copies are summed (the reference's semantics for a
+    # repeated index); duplicates_equal=True states that psi is a function of the state, so one copy is kept
+    table.build_lookup(g_keys, g_psi, duplicates_equal=duplicates_equal)
     eloc = table.local_energy(k, pc, out=out, rebuild_lookup=False)
     sums = reduce_stats(table.stats(eloc, weights_shard), group)
     return eloc, sums

@@ -63,17 +63,20 @@ class DeviceTermTable:
         return _lib.stream_ptr(self.device)
 
     # ------------------------------------------------------------------ amplitude lookup
-    def build_lookup(self, keys, psi, kind=LOOKUP_AUTO, assume_unique=False):
+    def build_lookup(self, keys, psi, kind=LOOKUP_AUTO, assume_unique=False, duplicates_equal=False):
         """(key, psi) pairs of the sampled batch -> device lookup structure (duplicates summed).
         assume_unique=True is the reference's own contract at the call site (energy.py:245 passes assume_unique=True): it
-        lets the dense table keep complex64 amplitudes as 8-byte entries."""
+        lets the dense table keep complex64 amplitudes as 8-byte entries.  duplicates_equal=True: keys may repeat but every
+        copy carries the same amplitude (psi is a function of the state, e.g. all-gathered shards of several ranks) — copies
+        are dropped instead of summed."""
         k = self._keys(keys)
         p, code = _lib.psi_to_device(psi, self.device)
         if p.shape[0] != k.shape[0]:
             raise ValueError("keys and psi must have the same length")
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().naqs_lookup_build(self._h, _lib.ptr(k), _lib.ptr(p), code, k.shape[0],
-                                                     kind | (_lib.LOOKUP_ASSUME_UNIQUE if assume_unique else 0), self._stream()),
+                                                     kind | (_lib.LOOKUP_ASSUME_UNIQUE if assume_unique else 0) |
+                                                     (_lib.LOOKUP_DUPLICATES_EQUAL if duplicates_equal else 0), self._stream()),
                        "naqs_lookup_build")
         self._lookup_built = True
         return self

@@ -218,6 +218,14 @@ def test_edge_cases():
     tp = eo.synthetic_psi(110, 9)
     e = gpu_eloc(t, sec[:100], tp[:100], table_keys=tk, table_psi=tp)
     assert rel_err(e, ct.local_energy(sec[:100], tp[:100], tk, tp)).max() <= 1e-11
+    # duplicates_equal: keys may repeat with the SAME amplitude (all-gathered shards) -> one copy kept, not summed
+    tk2 = np.concatenate([sec[:100], sec[:37], sec[5:60]])
+    tp2 = np.concatenate([tp[:100], tp[:37], tp[5:60]])
+    ref_u = ct.local_energy(sec[:100], tp[:100], sec[:100], tp[:100])
+    for kind in (nb200._lib.LOOKUP_DENSE, nb200._lib.LOOKUP_HASH):
+        t.build_lookup(tk2, tp2, kind=kind, duplicates_equal=True)
+        e = nb200._lib.complex_from_pairs(t.local_energy(sec[:100], tp[:100], rebuild_lookup=False))
+        assert rel_err(e, ref_u).max() <= ELOC_RTOL
     # a state outside the sector has no stored couplings (its couplings all fail the sector mask)
     bad = np.array([0b111], dtype=np.uint64)
     ip, _, _, _ = t.rows(bad)
