@@ -367,8 +367,8 @@ constexpr int kQueueCap = 16;  // pending couplings per thread (hash mode)
 // of the keys that occur as rows; the raw sums S[k] = sum_u H[k, k^u] psi(k^u) go to partial[chunk * M + k] and
 // eloc_rows_finalize_kernel turns them into E_loc per row.  A warp then holds 32 consecutive keys and every table
 // read of a group falls into one aligned 512-byte block: 4 L1 lines per request instead of ~11 scattered sectors.
-template <int NW, int NN, int THREADS, int LK, bool SEC, bool KEYORDER, bool PSI32>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
+template <int NW, int NN, int THREADS, int CTAS_PER_SM, int LK, bool SEC, bool KEYORDER, bool PSI32>
+__global__ void __launch_bounds__(THREADS, CTAS_PER_SM)
 eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint32_t queue_offset, uint32_t filter_offset, Sector sec, LookupView lv,
                    const uint64_t* __restrict__ states, const uint32_t* __restrict__ need, const void* __restrict__ psi,
                    int psi_dtype, int64_t M, double2* __restrict__ out, double2* __restrict__ partial) {

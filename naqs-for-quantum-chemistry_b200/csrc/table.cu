@@ -140,9 +140,14 @@ __global__ void dense_scatter_kernel(double2* dense, const uint64_t* __restrict_
 constexpr int kThreads = 256;
 
 // sliced kernel launch shapes: threads per CTA and shared-memory tile capacity (two buffers per CTA)
-constexpr int kSlicedThreads[3] = {1024, 512, 256};
-// tile capacities: [0..2] dense lookup, [3..5] hash lookup (which also keeps a 64 B/thread coupling queue in smem)
-constexpr size_t kSlicedCap[6] = {112640, 55296, 26624, 47104, 36864, 18432};  // hash/1024: 2 x 46 KB tiles + 64 KB queue + 64 KB filter
+// launch shapes [0..2] dense lookup: 1024/512/256 threads, 1/2/4 CTAs per SM (64 registers per thread);
+//               [3..5] hash lookup : same thread counts, smaller tiles: 64 B/thread coupling queue, and a 64 KB Bloom filter
+//                                    in the 1-CTA-per-SM shape.  (Measured alternatives: 512 x 1 CTA/SM with 128 registers
+//                                    1.70 ms, 896 threads 1.06 ms, 1024 threads 0.99 ms on Li2O 1e5 — occupancy wins.)
+constexpr int kSlicedThreads[6] = {1024, 512, 256, 1024, 512, 256};
+constexpr int kSlicedCtasPerSm[6] = {1, 2, 4, 1, 2, 4};
+constexpr bool kSlicedFilter[6] = {false, false, false, true, false, false};
+constexpr size_t kSlicedCap[6] = {112640, 55296, 26624, 47104, 36864, 18432};
 constexpr size_t kSlicedMaxBlob = 16384;
 
 static int tile_cap_for(int nw32, int64_t K) {
@@ -431,8 +436,8 @@ static int launch_sliced_cfg(naqs_table_t* t, const uint64_t* d_states, const vo
                              double* d_eloc, cudaStream_t stream, int n_chunks, int sm_count) {
     // key-order mode walks all 2^N keys; otherwise one thread per row
     const int64_t M = KEYORDER ? (1ll << t->n_qubits) : M_rows;
-    constexpr int THREADS = kSlicedThreads[CFG];
-    constexpr int TL = CFG + (LK == kLookHash ? 3 : 0);  // tile list of this launch shape
+    constexpr int TL = CFG + (LK == kLookHash ? 3 : 0);  // launch shape / tile list
+    constexpr int THREADS = kSlicedThreads[TL];
     const int n_tiles = t->n_stiles[TL];
     const int tiles_per_chunk = std::max(1, (n_tiles + n_chunks - 1) / n_chunks);
     n_chunks = std::max(1, (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk);
@@ -441,12 +446,12 @@ static int launch_sliced_cfg(naqs_table_t* t, const uint64_t* d_states, const vo
     const size_t queue_bytes = LK == kLookHash ? (size_t)kQueueCap * 4 * THREADS : 0;
     const size_t queue_offset = resident ? cap : 2 * cap;
     // the Bloom filter rides along only in the 1-CTA-per-SM shape (it needs 64 KB of shared memory)
-    const bool use_filter = LK == kLookHash && CFG == 0 && t->filter_valid;
+    const bool use_filter = kSlicedFilter[TL] && t->filter_valid;
     const size_t filter_offset = queue_offset + queue_bytes;
     const size_t smem = filter_offset + (use_filter ? kFilterBytes : 0);
-    auto kern = eloc_sliced_kernel<NW, NN, THREADS, LK, SEC, KEYORDER, PSI32>;
+    auto kern = eloc_sliced_kernel<NW, NN, THREADS, kSlicedCtasPerSm[TL], LK, SEC, KEYORDER, PSI32>;
     NAQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(2 * cap + queue_bytes + (LK == kLookHash && CFG == 0 ? kFilterBytes : 0))));
+                                   (int)(2 * cap + queue_bytes + (kSlicedFilter[TL] ? kFilterBytes : 0))));
     LookupView lv = t->lookup();
     if (!use_filter) lv.filter = nullptr;
     double2* partial = nullptr;
@@ -468,7 +473,7 @@ static int launch_sliced_cfg(naqs_table_t* t, const uint64_t* d_states, const vo
         }
     }
     const int64_t n_blocks = (M + THREADS - 1) / THREADS;
-    const int slots = sm_count * (1024 / THREADS);
+    const int slots = sm_count * kSlicedCtasPerSm[TL];
     dim3 grid((unsigned)std::min<int64_t>(n_blocks, slots), (unsigned)n_chunks);
     SlicedView sv{t->d_stream, (const STile*)t->d_stiles[TL], n_tiles, t->nn};
     kern<<<grid, THREADS, smem, stream>>>(sv, tiles_per_chunk, (uint32_t)cap, (uint32_t)queue_offset, (uint32_t)filter_offset, t->sector, lv, d_states, need_bits, d_psi, psi_dtype,
@@ -504,8 +509,8 @@ static int launch_sliced(naqs_table_t* t, const uint64_t* d_states, const void* 
     int cfg = 2, n_chunks = 1;
     double best_eff = -1.0;
     for (int c = 0; c < 3; ++c) {
-        const int64_t n_blocks = (M + kSlicedThreads[c] - 1) / kSlicedThreads[c];
-        const int64_t slots = (int64_t)sm_count * (1024 / kSlicedThreads[c]);
+        const int64_t n_blocks = (M + kSlicedThreads[c + tl_off] - 1) / kSlicedThreads[c + tl_off];
+        const int64_t slots = (int64_t)sm_count * kSlicedCtasPerSm[c + tl_off];
         const int max_chunks = n_blocks >= slots ? 1 : std::min(t->n_stiles[c + tl_off], 16);
         int ch_best = 1;
         double eff_best = -1.0;
