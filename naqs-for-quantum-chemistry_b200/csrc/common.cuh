@@ -5,7 +5,7 @@
 //   the reference, src/optimizer/hamiltonian.py:248), terms of a group in ascending reference index k,
 //   so a serial walk over a group reproduces the summation order of
 //   src_cpp/hamiltonian_math.pyx:31-34 bit for bit.
-//   Masks are held as NW32 32-bit words (NW32 = 1 for N<=32, 2 for N<=64, 4 for N<=128) in
+//   Masks are held as NW32 32-bit words (NW32 = 1 for N<=32, 2 for N<=63, 4 for N<=127) in
 //   struct-of-arrays form so that a warp reads one word per term with a single broadcast LDS.
 #pragma once
 #include <cuda_runtime.h>

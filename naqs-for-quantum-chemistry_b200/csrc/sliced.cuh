@@ -51,7 +51,7 @@ struct HostGroup {
     std::vector<double> c;
 };
 
-inline int nibbles_for(int n_qubits) { return n_qubits <= 20 ? 5 : (n_qubits <= 32 ? 8 : (n_qubits <= 64 ? 16 : 32)); }
+inline int nibbles_for(int n_qubits) { return n_qubits <= 20 ? 5 : (n_qubits <= 32 ? 8 : (n_qubits <= 63 ? 16 : 32)); }
 inline size_t rec_bytes_A(int nn, int nw) { return (size_t)64 * nn + 32 * nw + 8 * 16 * 8; }
 inline size_t rec_bytes_B(int nn, int nw) { return (size_t)64 * nn + 32 * nw + 5 * 64 * 8; }
 inline size_t rec_bytes_C(int nn) { return (size_t)64 * nn + 256; }

@@ -189,7 +189,8 @@ int naqs_table_create(naqs_table_t** out, const uint64_t* h_xy, const uint64_t* 
 
     auto* t = new naqs_table();
     t->device = device; t->words = words; t->n_qubits = n_qubits; t->n_alpha = n_alpha; t->n_beta = n_beta; t->K = K;
-    t->nw32 = n_qubits <= 32 ? 1 : (n_qubits <= 64 ? 2 : 4);
+    // keys of up to 63 bits take the bucketed hash (bit 63 is its overflow flag); 64..127 qubits use 128-bit keys
+    t->nw32 = n_qubits <= 32 ? 1 : (n_qubits <= 63 ? 2 : 4);
     const int NW = t->nw32;
 
     // group by XY mask: ascending multi-word value (np.unique), stable in k

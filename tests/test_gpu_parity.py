@@ -168,7 +168,7 @@ def test_rows_and_hij_vs_oracle_bit_exact(mol, m, sector):
     assert np.array_equal(uniq, np.unique(c2[:, 0]))
 
 
-@pytest.mark.parametrize("N,K,M", [(40, 1500, 3000), (63, 4000, 2000), (100, 3000, 2500), (127, 1000, 1000), (20, 30000, 500)])
+@pytest.mark.parametrize("N,K,M", [(40, 1500, 3000), (63, 4000, 2000), (64, 2000, 1500), (100, 3000, 2500), (127, 1000, 1000), (20, 30000, 500)])
 def test_wide_and_large_synthetic_tables(N, K, M):
     """64-/128-bit masks and tables larger than one shared-memory tile."""
     nb200, c_oracle, eo = _mods()
