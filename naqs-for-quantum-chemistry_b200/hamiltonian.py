@@ -99,6 +99,18 @@ class PauliHamiltonianB200:
                                       assume_unique=assume_unique)
         return _lib.complex_from_pairs(out) if ret_numpy else out
 
+    def local_energy_full(self, states_idx, psi, psi_fn):
+        """E_loc with the amplitudes of ALL coupled states, not only the sampled ones — the mode the reference leaves
+        unimplemented (`set_unsampled_states_to_zero=False` raises NotImplementedError, energy.py:250-258).
+        The sorted unique coupled set comes from the device (rows kernel + radix sort + unique, i.e.
+        get_coupled_state_idxs(return_unique=True) of hamiltonian.py:122-132); `psi_fn(keys int64 [U]) -> complex [U]`
+        evaluates the wavefunction on it (one batched network call); the fused kernel then runs against that table."""
+        keys = np.asarray(states_idx).reshape(-1).astype(np.int64) if not torch.is_tensor(states_idx) else states_idx.reshape(-1).cpu().numpy().astype(np.int64)
+        coupled = self.table.coupled_state_set(keys)[:, 0].cpu().numpy()
+        psi_c = np.asarray(psi_fn(coupled))
+        out = self.table.local_energy(keys, psi, table_keys=coupled, table_psi=psi_c, assume_unique=True)
+        return _lib.complex_from_pairs(out)
+
     def linear_operator(self, states_idx):
         """scipy LinearOperator of H restricted to the given basis states, applied matrix-free on the device."""
         from scipy.sparse.linalg import LinearOperator

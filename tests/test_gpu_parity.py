@@ -515,3 +515,30 @@ def test_matrix_free_apply_h_and_ground_state():
                                     restricted_idxs=hil.get_subspace(ret_states=False, ret_idxs=True), dtype=np.float64)
     e0, _ = ph.solve_H(hil.get_subspace(ret_states=False, ret_idxs=True).numpy())
     assert abs(e0[0] - known["LiH"]["e0"]) < 1e-8
+
+
+def test_local_energy_with_unsampled_amplitudes():
+    """E_loc with psi evaluated on the deduplicated coupled set (the mode the reference leaves
+    unimplemented).  For a batch that is a strict subset of the sector, it must equal (H psi)[s] / psi[s] over the FULL sector."""
+    import types
+    from conftest import load_terms_json
+    nb200, c_oracle, eo = _mods()
+    N, na, nb = 12, 2, 2
+    hil = nb200.Hilbert.get(N, na, nb, encoding=nb200.Encoding.SIGNED)
+    sec = hil.get_subspace(ret_states=False, ret_idxs=True).numpy().astype(np.int64)
+    ph = nb200.PauliHamiltonian.get(hil, types.SimpleNamespace(terms=load_terms_json("LiH")), restricted_idxs=sec, dtype=np.float64)
+    rng = np.random.default_rng(4)
+    psi_all = (rng.normal(size=len(sec)) + 1j * rng.normal(size=len(sec))).astype(np.complex64)
+    lut = {int(k): psi_all[i] for i, k in enumerate(sec)}
+    batch = rng.permutation(len(sec))[:40]
+    calls = []
+
+    def psi_fn(keys):
+        calls.append(len(keys))
+        return np.array([lut[int(k)] for k in keys], dtype=np.complex64)
+
+    e = ph.local_energy_full(sec[batch], psi_all[batch], psi_fn)
+    xy, yz, c, *_ = load_table("LiH")
+    ref = c_oracle.COracleTable(xy, yz, c, N, na, nb).local_energy(sec[batch].astype(np.uint64), psi_all[batch], sec.astype(np.uint64), psi_all)
+    assert len(calls) == 1 and calls[0] <= len(sec)
+    assert rel_err(e, ref).max() <= ELOC_RTOL
