@@ -379,7 +379,7 @@ def synthetic_table(n_qubits, n_terms, seed=0, group_ratio=6.0):
     n_groups = max(2, int(n_terms / group_ratio))
     flips = [0]
     for _ in range(n_groups - 1):
-        nb = 2 if rng.random() < 0.3 else 4
+        nb = min(2 if rng.random() < 0.3 else 4, n_qubits)
         qs = rng.choice(n_qubits, nb, replace=False)
         flips.append(sum(1 << int(q) for q in qs))
     xy, yz = [], []

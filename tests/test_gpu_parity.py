@@ -542,3 +542,27 @@ def test_local_energy_with_unsampled_amplitudes():
     ref = c_oracle.COracleTable(xy, yz, c, N, na, nb).local_energy(sec[batch].astype(np.uint64), psi_all[batch], sec.astype(np.uint64), psi_all)
     assert len(calls) == 1 and calls[0] <= len(sec)
     assert rel_err(e, ref).max() <= ELOC_RTOL
+
+
+@pytest.mark.parametrize("N,K,M", [(2, 3, 4), (4, 15, 16), (5, 40, 20), (21, 800, 3000), (22, 800, 3000), (23, 800, 3000), (31, 600, 2000),
+                                   (32, 600, 2000), (33, 600, 2000)])
+def test_boundary_widths_and_tiny_spaces(N, K, M):
+    """Key widths around every dispatch boundary (dense <-> hash at 22/23 qubits, 32-bit <-> 64-bit masks at 32/33, nibble
+    counts 5/8/16) and spaces so small that the whole space is the batch (key-order walk with a handful of keys)."""
+    nb200, c_oracle, eo = _mods()
+    xy, yz, c = eo.synthetic_table(N, K, seed=1000 + N)
+    M = min(M, 2 ** N)
+    if 2 ** N <= 4 * M:
+        st = np.random.default_rng(N).permutation(2 ** N)[:M].astype(np.uint64)
+    else:
+        st = eo.synthetic_states(N, M, seed=N)[:, 0]
+    psi = eo.synthetic_psi(len(st), seed=N)
+    t, ct = nb200.DeviceTermTable(xy, yz, c, N), c_oracle.COracleTable(xy, yz, c, N)
+    ref = ct.local_energy(st, psi)
+    for kw in ({}, {"assume_unique": True}, {"kind": nb200._lib.LOOKUP_HASH}):
+        assert rel_err(gpu_eloc(t, st, psi, **kw), ref).max() <= ELOC_RTOL, kw
+    t.set_algo("direct")
+    assert rel_err(gpu_eloc(t, st, psi), ref).max() <= ELOC_RTOL
+    indptr, cols, _, vals = t.rows(st[:64], with_restricted_index=False)
+    i2, c2, v2 = ct.rows(st[:64])
+    assert np.array_equal(indptr.cpu().numpy(), i2) and np.array_equal(cols.cpu().numpy().view(np.uint64), c2) and np.array_equal(vals.cpu().numpy(), v2)
