@@ -374,9 +374,11 @@ def main():
     d_eloc = torch.empty((M, 2), dtype=torch.float64, device=dev)
     h_eloc = torch.empty((M, 2), dtype=torch.float64).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    allreduce_table = world > 1 and naqs_b200.distributed.can_allreduce_table(table, d_psi) and not os.environ.get("NAQS_BENCH_ALLGATHER")
     if world > 1:
         g_states = torch.empty((world * M, W), dtype=torch.int64, device=dev)
         g_psi = torch.empty(world * M, dtype=torch.complex64, device=dev)
+        dense_tbl = torch.empty((1 << wl["N"], 2), dtype=torch.int32, device=dev) if allreduce_table else None
     dedup = wl.get("dedup_table", False)
     if dedup:  # H2O "with replacement" workload: the lookup table is the distinct keys (fixed across steps)
         uk, first = np.unique(wl["states"], return_index=True)
@@ -385,10 +387,13 @@ def main():
 
     def step(states, psi, out):
         """One pass of the hot path with device-resident inputs; returns the 5 statistics sums (device)."""
-        if world > 1:
-            # public multi-GPU API: all-gather (key, psi) -> lookup build -> fused E_loc on the shard -> all-reduce of 5 sums
+        if world > 1 and allreduce_table:
+            # small key space: the direct-address table itself is all-reduced (8 * 2^N bytes, independent of the rank count);
+            # psi is a function of the state, so copies of a key on several ranks are identical
+            naqs_b200.distributed.allreduce_dense_table(table, states, psi, out=dense_tbl)
+        elif world > 1:
+            # all-gather (key, psi) -> lookup build (one amplitude per key) -> fused E_loc on the shard -> all-reduce of 5 sums
             g_k, g_p, _ = naqs_b200.distributed.gather_table(states, psi, equal_sizes=True, out=(g_states, g_psi))
-            # ranks may have sampled the same configuration; psi is a function of the state, so one copy per key is kept
             table.build_lookup(g_k, g_p, duplicates_equal=True)
         elif dedup:
             table.build_lookup(t_keys, t_psi, assume_unique=True)
@@ -522,7 +527,7 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": wl["desc"], "states_per_gpu": M, "terms": K, "lookup_keys": T,
-                       "parallelism": f"states sharded x{world}, Pauli table replicated" + (", NCCL all-gather of (key, psi) + all-reduce of 5 fp64 sums" if world > 1 else ""),
+                       "parallelism": f"states sharded x{world}, Pauli table replicated" + ((", NCCL all-reduce (MAX) of the 2^N-entry complex64 amplitude table" if allreduce_table else ", NCCL all-gather of (key, psi)") + " + all-reduce of 5 fp64 sums" if world > 1 else ""),
                        "l2": "256 MB device memset between timed steps (L2 flush, untimed)", "timing": "CUDA events per step on the launching stream, max over ranks"},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_pipe": roofline_pipe,
             "cpu_baseline": cpu, "other_configs": extras,

@@ -88,6 +88,17 @@ int naqs_table_info(const naqs_table_t* t, int64_t* info8);
 int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi, int psi_dtype,
                       int64_t n_keys, int kind, void* stream);
 
+/* Dense complex64 table owned by the CALLER (multi-GPU: the direct-address table itself is all-reduced over NVLink
+ * instead of all-gathering the (key, psi) pairs — constant volume 8 * 2^n bytes, independent of the number of ranks):
+ *   1. fill the table with -0.0f (bit pattern 0x80000000 = INT32_MIN; it acts as "absent" AND as a numeric zero),
+ *   2. naqs_dense32_scatter: table[key] = psi for the rank's own pairs (plain stores),
+ *   3. all-reduce MAX over the table viewed as int32 — any present bit pattern beats INT32_MIN, and copies of a key are
+ *      equal by contract (psi is a function of the state),
+ *   4. naqs_lookup_attach_dense32: naqs_eloc / naqs_apply_h then read this table (key-order walk).
+ * The table must stay alive until the next naqs_lookup_build / attach. */
+int naqs_dense32_scatter(float* d_table /* [2^n][2] */, const uint64_t* d_keys, const void* d_psi_c64, int64_t n_keys, void* stream);
+int naqs_lookup_attach_dense32(naqs_table_t* t, const float* d_table, int64_t n_entries);
+
 /* ------------------------------------------------------------------------------------------
  * Fused local energy — replaces OptimizerBase.calculate_local_energy's body
  * (src/optimizer/energy.py:245-248): update_H + get_H + sparse_dense_mv + "/ psi" + conj.

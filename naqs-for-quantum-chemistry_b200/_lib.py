@@ -32,6 +32,8 @@ SIGNATURES = {
     "naqs_eloc": (_i, [_p, _p, _p, _i, _i64, _p, _p]),
     "naqs_table_set_algo": (_i, [_p, _i]),
     "naqs_apply_h": (_i, [_p, _p, _i64, _p, _p]),
+    "naqs_dense32_scatter": (_i, [_p, _p, _p, _i64, _p]),
+    "naqs_lookup_attach_dense32": (_i, [_p, _p, _i64]),
     "naqs_eloc_host": (_i, [_p, _p, _i, _p, _i, _i64, _p, _p, _i64, _i, _p, _i]),
     "naqs_rows_count": (_i, [_p, _p, _i64, _p, _p]),
     "naqs_exclusive_scan": (_i, [_p, _p, _i64, _p, _p]),

@@ -172,6 +172,7 @@ struct naqs_table {
     int64_t lookup_n = 0;
     double2* d_dense = nullptr;
     int64_t dense_entries = 0;
+    const float2* d_dense32_ext = nullptr;  // caller-owned complex64 dense table (naqs_lookup_attach_dense32), e.g. all-reduced
     float2* d_dense32 = nullptr;   // complex64 dense table (key-order walk with unique complex64 amplitudes)
     int64_t dense32_entries = 0;
     bool dense32_valid = false;
@@ -198,7 +199,8 @@ struct naqs_table {
         for (int64_t c = n_buckets; c > 1; c >>= 1) --bshift;
         return naqs::LookupView{d_dense, d_slots, (unsigned long long)(hash_cap - 1), lookup_kind, shift,
                                 d_buckets, (unsigned)(n_buckets > 0 ? n_buckets - 1 : 0), bshift,
-                                filter_valid ? d_filter : nullptr, dense32_valid ? d_dense32 : nullptr};
+                                filter_valid ? d_filter : nullptr,
+                                dense32_valid ? (d_dense32_ext ? d_dense32_ext : d_dense32) : nullptr};
     }
 };
 

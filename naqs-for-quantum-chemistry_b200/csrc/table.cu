@@ -328,6 +328,7 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
     kind &= 0xff;
     if (kind == NAQS_LOOKUP_AUTO) kind = (t->n_qubits <= 22) ? NAQS_LOOKUP_DENSE : NAQS_LOOKUP_HASH;
     t->dense32_valid = false;
+    t->d_dense32_ext = nullptr;
     NAQS_REQUIRE(kind == NAQS_LOOKUP_DENSE || kind == NAQS_LOOKUP_HASH, NAQS_ERR_ARG, "naqs_lookup_build: bad kind");
     const int blocks = (int)((n + 255) / 256);
     if (kind == NAQS_LOOKUP_DENSE || t->nw32 > 2) t->filter_valid = false;
@@ -594,6 +595,28 @@ int naqs_eloc(naqs_table_t* t, const uint64_t* d_states, const void* d_psi, int 
         case 2: return launch_eloc<2>(t, d_states, d_psi, psi_dtype, M, d_eloc, stream);
         default: return launch_eloc<4>(t, d_states, d_psi, psi_dtype, M, d_eloc, stream);
     }
+}
+
+int naqs_dense32_scatter(float* d_table, const uint64_t* d_keys, const void* d_psi, int64_t n, void* stream) {
+    NAQS_REQUIRE(n >= 0 && (n == 0 || (d_table && d_keys && d_psi)), NAQS_ERR_ARG, "naqs_dense32_scatter: NULL buffers");
+    if (n == 0) return NAQS_OK;
+    dense_scatter32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2*>(d_table), d_keys,
+                                                                                        reinterpret_cast<const float2*>(d_psi), n);
+    NAQS_LAUNCHED();
+    return NAQS_OK;
+}
+
+int naqs_lookup_attach_dense32(naqs_table_t* t, const float* d_table, int64_t entries) {
+    NAQS_REQUIRE(t && d_table, NAQS_ERR_ARG, "naqs_lookup_attach_dense32: NULL argument");
+    NAQS_REQUIRE(t->nw32 == 1 && t->n_qubits <= 26 && entries == (1ll << t->n_qubits), NAQS_ERR_ARG,
+                 "naqs_lookup_attach_dense32: the table must have exactly 2^n_qubits entries (n_qubits <= 26)");
+    NAQS_REQUIRE(t->algo == 0, NAQS_ERR_STATE, "naqs_lookup_attach_dense32: needs the sliced formulation");
+    t->lookup_kind = NAQS_LOOKUP_DENSE;
+    t->lookup_n = entries;
+    t->d_dense32_ext = reinterpret_cast<const float2*>(d_table);
+    t->dense32_valid = true;
+    t->filter_valid = false;
+    return NAQS_OK;
 }
 
 int naqs_apply_h(naqs_table_t* t, const uint64_t* d_states, int64_t M, double* d_out, void* stream_) {

@@ -70,6 +70,36 @@ def gather_table(keys, psi, group=None, equal_sizes=False, out=None):
     return g_keys, g_psi, sum(counts)
 
 
+INT32_MIN = -(2 ** 31)  # bit pattern of -0.0f: "absent" for the MAX all-reduce and a numeric zero for the kernel
+
+
+def can_allreduce_table(table, psi):
+    """The dense complex64 table can itself be all-reduced when the key space is small (N <= 22) and psi is complex64."""
+    return table.n_qubits <= 22 and table.words == 1 and psi.dtype == torch.complex64
+
+
+def allreduce_dense_table(table, keys, psi, group=None, out=None):
+    """Multi-GPU lookup build for small key spaces WITHOUT gathering the pairs: every rank scatters its own (key, psi) into a
+    direct-address complex64 table pre-filled with -0.0f, the tables are all-reduced with MAX on their int32 bit patterns
+    (NCCL over NVLink / NVSwitch, in-switch reduction where available), and the result is attached as the lookup table.
+    Volume: 8 * 2^N bytes per rank whatever the number of ranks (an all-gather moves 16 * M * world).  Requires psi to be a
+    function of the state (copies of a key on several ranks are identical): the same contract as duplicates_equal."""
+    from . import _lib
+    n_entries = 1 << table.n_qubits
+    if out is None:
+        out = torch.empty((n_entries, 2), dtype=torch.int32, device=table.device)
+    out.fill_(INT32_MIN)
+    k = keys if keys.dim() == 2 else keys.reshape(-1, 1)
+    with torch.cuda.device(table.device):
+        _lib.check(_lib.load().naqs_dense32_scatter(_lib.ptr(out), _lib.ptr(k), _lib.ptr(torch.view_as_real(psi.contiguous())), k.shape[0],
+                                                    _lib.stream_ptr(table.device)), "naqs_dense32_scatter")
+    world, _ = _world(group)
+    if world > 1:
+        dist.all_reduce(out, op=dist.ReduceOp.MAX, group=group)
+    table.attach_dense32(out)
+    return out
+
+
 def reduce_stats(sums5, group=None):
     """All-reduce (sum) the five statistics sums; returns the reduced tensor (in place)."""
     world, _ = _world(group)
@@ -89,6 +119,10 @@ def sharded_local_energy(table, keys_shard, psi_shard, weights_shard=None, group
     k = _lib.keys_to_device(keys_shard, table.words, table.device)
     p, _ = _lib.psi_to_device(psi_shard, table.device)
     pc = torch.view_as_complex(p)
+    if duplicates_equal and can_allreduce_table(table, pc):
+        allreduce_dense_table(table, k, pc, group)
+        eloc = table.local_energy(k, pc, out=out, rebuild_lookup=False)
+        return eloc, reduce_stats(table.stats(eloc, weights_shard), group)
     g_keys, g_psi, _ = gather_table(k, pc, group, equal_sizes=equal_sizes, out=gather_out)
     # several ranks may have sampled the same configuration: by default copies are summed (the reference's semantics for a
     # repeated index); duplicates_equal=True states that psi is a function of the state, so one copy is kept

@@ -81,6 +81,15 @@ class DeviceTermTable:
         self._lookup_built = True
         return self
 
+    def attach_dense32(self, table_tensor):
+        """Use a caller-owned complex64 direct-address table (float32 [2^N, 2] CUDA tensor, absent = -0.0) as the lookup."""
+        if table_tensor.dtype not in (torch.float32, torch.int32) or table_tensor.numel() != 2 * (1 << self.n_qubits):
+            raise ValueError("dense32 table must be float32/int32 [2^N, 2]")
+        _lib.check(_lib.load().naqs_lookup_attach_dense32(self._h, _lib.ptr(table_tensor), 1 << self.n_qubits), "naqs_lookup_attach_dense32")
+        self._dense32_keepalive = table_tensor
+        self._lookup_built = True
+        return self
+
     # ------------------------------------------------------------------ fused E_loc (Level-1)
     def local_energy(self, states, psi, table_keys=None, table_psi=None, kind=LOOKUP_AUTO, out=None, rebuild_lookup=True,
                      assume_unique=False):

@@ -82,3 +82,45 @@ def test_single_process_is_identity():
     assert total == 6 and torch.equal(g_keys, keys) and torch.equal(g_psi, psi)
     s = torch.arange(5, dtype=torch.float64)
     assert torch.equal(nd.reduce_stats(s.clone()), s)
+
+
+def _maxtrick_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_keys = 64
+        rng = np.random.default_rng(7)                       # same generator on every rank: psi is a function of the key
+        psi_all = (rng.normal(size=n_keys) + 1j * rng.normal(size=n_keys)).astype(np.complex64)
+        psi_all[3] = np.complex64(complex(-0.0, 1.5))        # a component that IS -0.0 (collides with the "absent" pattern)
+        mine = np.random.default_rng(50 + rank).permutation(n_keys)[:40]      # overlapping shards
+        tbl = torch.full((n_keys, 2), nd.INT32_MIN, dtype=torch.int32)
+        bits = torch.from_numpy(np.ascontiguousarray(psi_all[mine]).view(np.float32).reshape(-1, 2).view(np.int32).copy())
+        tbl[torch.from_numpy(mine)] = bits                   # what naqs_dense32_scatter does on the device
+        dist.all_reduce(tbl, op=dist.ReduceOp.MAX)
+        q.put((rank, mine, tbl.numpy().copy(), psi_all))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allreduce_max_on_float_bit_patterns_world2():
+    """The dense-table all-reduce: MAX over int32 bit patterns with -0.0f (INT32_MIN) as "absent" reproduces the union of
+    the ranks' (key, psi) sets exactly — including negative amplitudes — and absent entries stay numeric zeros."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_maxtrick_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(world)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    union = np.union1d(res[0][1], res[1][1])
+    psi_all = res[0][3]
+    for _, _, tbl, _ in res:
+        got = tbl.view(np.float32).view(np.complex64).reshape(-1)
+        assert np.array_equal(got[union], psi_all[union])                    # value-equal (-0.0 == 0.0)
+        absent = np.setdiff1d(np.arange(64), union)
+        assert np.all(got[absent] == 0)
+        assert np.array_equal(res[0][2], tbl)                                 # every rank ends with the same table

@@ -459,6 +459,11 @@ def _mgpu_worker(rank, world, port, q):
         psi = (rng.normal(size=len(st)) + 1j * rng.normal(size=len(st))).astype(np.complex64)
         lo, hi = nd.shard_bounds(len(st), world, rank)
         eloc, stats = nd.sharded_local_energy_stats(t, st[lo:hi], psi[lo:hi])
+        # same through the all-reduced dense table (psi is a function of the state: duplicates_equal)
+        eloc2, sums2 = nd.sharded_local_energy(t, st[lo:hi], psi[lo:hi], duplicates_equal=True)
+        assert nd.can_allreduce_table(t, torch.from_numpy(psi))
+        diff = float((eloc2 - eloc).abs().max() / eloc.abs().max())
+        assert diff < 1e-13, diff
         q.put((rank, lo, hi, naqs_b200._lib.complex_from_pairs(eloc), stats))
         dist.barrier()
     finally:
