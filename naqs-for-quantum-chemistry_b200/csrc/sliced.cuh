@@ -219,10 +219,6 @@ __device__ __forceinline__ uint32_t parity_word(const unsigned char* __restrict_
 // ------------------------------------------------------------------------------------------ kernel
 constexpr int kLookDense = 0, kLookHash = 1;
 
-// Accumulate H[b] * psi_table(s ^ u_b) for a batch of B groups.  All B table reads are issued before any
-// is consumed (memory-level parallelism); lanes whose H is exactly 0.0 (hamiltonian.py:363) or whose coupled
-// state leaves the sector (hamiltonian.py:328) read entry 0 / slot 0 instead — a single broadcast sector —
-// and contribute H * psi = 0 exactly, so no branch is needed.
 // 64-bit address of entry `key` of the dense table with ONE instruction (IMAD.WIDE.U32 on the FMA pipe)
 __device__ __forceinline__ const double2* dense_entry(const double2* __restrict__ base, uint32_t key) {
     unsigned long long addr;
@@ -236,6 +232,10 @@ __device__ __forceinline__ const float2* dense_entry32(const float2* __restrict_
     return reinterpret_cast<const float2*>(addr);
 }
 
+// Accumulate H[b] * psi_table(s ^ u_b) for a batch of B groups (dense lookup).  All B table reads are issued before any
+// is consumed (memory-level parallelism); lanes whose H is exactly 0.0 (hamiltonian.py:363) or whose coupled
+// state leaves the sector (hamiltonian.py:328) read entry 0 / slot 0 instead — a single broadcast sector —
+// and contribute H * psi = 0 exactly, so no branch is needed.
 template <int NW, bool SEC, bool KEYORDER, bool PSI32, int B>
 __device__ __forceinline__ void emit_batch(const double (&h)[B], const uint32_t (&u)[B], const uint32_t (&s)[NW],
                                            bool valid, const Sector& sec, const LookupView& lv, double& e_re, double& e_im) {
@@ -281,8 +281,9 @@ __device__ __forceinline__ void emit_batch(const double (&h)[B], const uint32_t 
     }
 }
 
-// Hash-lookup ("heavy") epilogue of up to B couplings of one thread: sector filter (hamiltonian.py:328), probe of the
-// 32-byte-slot hash table, complex multiply-add.  Called only for couplings whose H is not exactly 0.0
+// Hash-lookup ("heavy") epilogue of up to B couplings of one thread: sector filter (hamiltonian.py:328), shared-memory
+// Bloom filter when the launch shape carries one, probe of the bucketed table (keys <= 63 bits: one 256-bit load reads
+// the four keys of a 128-byte bucket) or of the 32-byte-slot table (wider keys), complex multiply-add.  Called only for couplings whose H is not exactly 0.0
 // (hamiltonian.py:363), which the per-thread queue of the kernel below makes dense across the warp.  The first probes
 // of all B couplings are issued before any is examined, so their L2 latencies overlap.
 template <int NW, bool SEC, int B>
