@@ -378,7 +378,7 @@ def main():
     if world > 1:
         g_states = torch.empty((world * M, W), dtype=torch.int64, device=dev)
         g_psi = torch.empty(world * M, dtype=torch.complex64, device=dev)
-        dense_tbl = torch.empty((1 << wl["N"], 2), dtype=torch.int32, device=dev) if allreduce_table else None
+        dense_tbl = naqs_b200.distributed.aligned_dense_table(table) if allreduce_table else None
     dedup = wl.get("dedup_table", False)
     if dedup:  # H2O "with replacement" workload: the lookup table is the distinct keys (fixed across steps)
         uk, first = np.unique(wl["states"], return_index=True)

@@ -95,7 +95,8 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
  *   3. all-reduce MAX over the table viewed as int32 — any present bit pattern beats INT32_MIN, and copies of a key are
  *      equal by contract (psi is a function of the state),
  *   4. naqs_lookup_attach_dense32: naqs_eloc / naqs_apply_h then read this table (key-order walk).
- * The table must stay alive until the next naqs_lookup_build / attach. */
+ * The table must stay alive until the next naqs_lookup_build / attach, and its address must be a multiple of its size
+ * (8 * 2^n bytes): the kernel forms entry addresses with XORs, (base ^ key * 8) ^ (flip * 8). */
 int naqs_dense32_scatter(float* d_table /* [2^n][2] */, const uint64_t* d_keys, const void* d_psi_c64, int64_t n_keys, void* stream);
 int naqs_lookup_attach_dense32(naqs_table_t* t, const float* d_table, int64_t n_entries);
 
@@ -122,6 +123,15 @@ int naqs_apply_h(naqs_table_t* t, const uint64_t* d_states, int64_t n_states, do
  * AND/POPC walk (the formulation of hamiltonian_math.pyx:449-451, 31-34 transcribed; kept for A/B checks).
  * Both give bit-identical H_ij.  The environment variable NAQS_ELOC_ALGO=direct sets the default. */
 int naqs_table_set_algo(naqs_table_t* t, int algo);
+
+/* Accumulation type of H_ij: 64 (default) = float64, the type the reference's experiments run with
+ * (experiments/_base.py:234); 32 = float32, the constructor default of PauliHamiltonian.get (src/optimizer/hamiltonian.py:48):
+ * the coefficients must already be float32 values (couplings.astype(np.float32), hamiltonian.py:424) and every partial
+ * sum is rounded to float32 exactly as in __inner_int64_float (src_cpp/hamiltonian_math.pyx:60-100 family), so H_ij is
+ * bit-identical to the reference's float32 matrix.  E_loc itself is still accumulated in complex128 (the reference uses
+ * complex64 there, sparse_math.pyx:13-41) — within float32 rounding of it.  A float32 table runs the direct formulation.
+ * bits other than 32 / 64 (np.float128) -> NAQS_ERR_DTYPE. */
+int naqs_table_set_precision(naqs_table_t* t, int bits);
 
 /* Same through HOST buffers (what a caller holding numpy arrays / CPU tensors uses; bench.py's e2e leg): uploads
  * states + psi, builds the lookup table, runs naqs_eloc and downloads E_loc.  Synchronous.

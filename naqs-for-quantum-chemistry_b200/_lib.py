@@ -31,6 +31,7 @@ SIGNATURES = {
     "naqs_lookup_build": (_i, [_p, _p, _p, _i, _i64, _i, _p]),
     "naqs_eloc": (_i, [_p, _p, _p, _i, _i64, _p, _p]),
     "naqs_table_set_algo": (_i, [_p, _i]),
+    "naqs_table_set_precision": (_i, [_p, _i]),
     "naqs_apply_h": (_i, [_p, _p, _i64, _p, _p]),
     "naqs_dense32_scatter": (_i, [_p, _p, _p, _i64, _p]),
     "naqs_lookup_attach_dense32": (_i, [_p, _p, _i64]),

@@ -71,6 +71,7 @@ struct TableView {
     const uint32_t* gxy;     // [NW32][G]
     const uint32_t* gstart;  // [G+1]       term offsets of each group
     int K, G;
+    int f32;                 // 1: every partial sum of H_ij is rounded to float32 (the reference's dtype=np.float32 kernel)
 };
 
 // A shared-memory tile of the term table: terms [t0, t1) and the groups touching them [g0, g1).
@@ -160,6 +161,8 @@ struct naqs_table {
     long long* d_binom = nullptr;  // C(n, k) table for the restricted-index ranker (lazy)
     // sliced (v2) formulation: byte stream + tile lists for the 1024/512/256-thread launch shapes
     int algo = 0;                  // 0 = sliced (default), 1 = direct
+    int f32 = 0;                   // naqs_table_set_precision(32): float32 accumulation of H_ij (direct formulation only)
+    bool coeff_f32_exact = false;  // every coefficient is representable in float32
     unsigned char* d_stream = nullptr;
     size_t stream_bytes = 0;
     void* d_stiles[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [0..2] dense, [3..5] hash tile lists
@@ -173,7 +176,8 @@ struct naqs_table {
     double2* d_dense = nullptr;
     int64_t dense_entries = 0;
     const float2* d_dense32_ext = nullptr;  // caller-owned complex64 dense table (naqs_lookup_attach_dense32), e.g. all-reduced
-    float2* d_dense32 = nullptr;   // complex64 dense table (key-order walk with unique complex64 amplitudes)
+    float2* d_dense32 = nullptr;   // complex64 dense table (key-order walk with unique complex64 amplitudes), aligned to its size
+    void* d_dense32_raw = nullptr; // the allocation d_dense32 points into
     int64_t dense32_entries = 0;
     bool dense32_valid = false;
     naqs::HashSlot* d_slots = nullptr;     // 128-bit keys: 32 B slots, linear probing
@@ -191,7 +195,7 @@ struct naqs_table {
     size_t pinned_bytes = 0;
     cudaStream_t own_stream = nullptr;
 
-    naqs::TableView view() const { return naqs::TableView{d_yz, d_coeff, d_gxy, d_gstart, (int)K, (int)G}; }
+    naqs::TableView view() const { return naqs::TableView{d_yz, d_coeff, d_gxy, d_gstart, (int)K, (int)G, f32}; }
     naqs::LookupView lookup() const {
         int shift = 32;
         for (int64_t c = hash_cap; c > 1; c >>= 1) --shift;

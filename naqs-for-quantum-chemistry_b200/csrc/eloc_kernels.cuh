@@ -197,6 +197,9 @@ __device__ __forceinline__ void walk_table(const TableView& tv, const Tile* __re
 #pragma unroll
                     for (int w = 1; w < NW; ++w) f ^= s[r][w] & yz[w];
                     acc[r] = __dadd_rn(acc[r], signed_coeff(c_hi, c_lo, f));
+                    // float32 table (hamiltonian_math.pyx __inner_int64_float): both operands are float32 values, so
+                    // rounding their double sum to float32 equals the float32 addition (53 >= 2*24 + 2 bits)
+                    if (tv.f32) acc[r] = (double)__double2float_rn(acc[r]);
                 }
             }
             if (ge <= tile.t1) {  // group complete (a straddling group continues in the next tile)

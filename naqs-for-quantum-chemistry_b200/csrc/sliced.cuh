@@ -10,12 +10,17 @@
 // is read from a 16- (64-) entry table indexed by those parity bits.  Every table entry was produced by
 // the same serial fp64 additions, in the same order, as the reference performs — so H is bit-identical —
 // but the device does one LDS.64 instead of n x (POPC, XOR, DADD).  Larger groups (the diagonal, the
-// 2-flip groups) keep the serial walk, their signs taken from the parity word (shift + XOR + DADD).
+// 2-flip groups) are cut into consecutive chunks of 6 terms with one 64-entry table each; the kernel adds the
+// chunk sums in term order (one LDS.64 + DADD per 6 terms).  That re-associates the reference's serial sum at
+// the chunk boundaries: H of a big group agrees with the reference to a few ulp, not bit for bit — E_loc is
+// specified to 1e-12 relative; the direct formulation (rows / CSR / hij_dense, NAQS_ELOC_ALGO=direct) keeps the
+// fully serial order and is bit-exact for every group.
 //
 // Stream layout (device memory, staged into shared memory tile by tile with cp.async.bulk + mbarrier):
-//   A record (8 groups x 4 bits):  T[NN][16] u32 | U[8][NW] u32 | LUT[8][16] f64
-//   B record (5 groups x 6 bits):  T[NN][16] u32 | U[8][NW] u32 | LUT[5][64] f64
-//   C blob   (one big group)    :  header{n_words, n_sub8, flags, -, u[4]} | n_words x ( T[NN][16] u32 | c[32] f64 )
+//   A record (8 groups x 4 bits):  T[NN][16] u32 | U[8][NW] u32 (+ U << 3 when NW == 1) | LUT[8][16] f64
+//   B record (5 groups x 6 bits):  T[NN][16] u32 | U[8][NW] u32 (+ U << 3 when NW == 1) | LUT[5][64] f64
+//   C blob   (<= 150 terms of one big group; a longer group is several blobs with the same u, each contributing
+//             H_blob * psi(s ^ u) on its own):  header{n_words, -, -, -, u[4]} | n_words x ( T[NN][16] u32 | LUT[5][64] f64 )
 #pragma once
 #include <algorithm>
 #include <cstring>
@@ -27,7 +32,6 @@
 namespace naqs {
 
 enum { kSecA = 0, kSecB = 1, kSecC = 2 };
-constexpr uint32_t kBlobFirst = 1u, kBlobLast = 2u;
 
 struct STile {
     uint32_t kind;      // kSecA / kSecB / kSecC
@@ -52,9 +56,12 @@ struct HostGroup {
 };
 
 inline int nibbles_for(int n_qubits) { return n_qubits <= 20 ? 5 : (n_qubits <= 32 ? 8 : (n_qubits <= 63 ? 16 : 32)); }
-inline size_t rec_bytes_A(int nn, int nw) { return (size_t)64 * nn + 32 * nw + 8 * 16 * 8; }
-inline size_t rec_bytes_B(int nn, int nw) { return (size_t)64 * nn + 32 * nw + 5 * 64 * 8; }
-inline size_t rec_bytes_C(int nn) { return (size_t)64 * nn + 256; }
+// flip masks of a record: 8 slots of nw words; single-word keys carry a second copy shifted left by 3 (= byte offsets into
+// the complex64 direct-address table, whose base is aligned to its size: entry address = (base ^ key * 8) ^ (u * 8))
+inline size_t u_bytes(int nw) { return nw == 1 ? 64 : (size_t)32 * nw; }
+inline size_t rec_bytes_A(int nn, int nw) { return (size_t)64 * nn + u_bytes(nw) + 8 * 16 * 8; }
+inline size_t rec_bytes_B(int nn, int nw) { return (size_t)64 * nn + u_bytes(nw) + 5 * 64 * 8; }
+inline size_t rec_bytes_C(int nn) { return (size_t)64 * nn + 5 * 64 * 8; }  // one word of a big group: 5 chunks of <= 6 terms
 constexpr size_t kBlobHeader = 32;
 
 struct SlicedHost {
@@ -111,13 +118,14 @@ inline void build_sliced_host(const std::vector<HostGroup>& groups, int n_qubits
             unsigned char* p = S.data() + base + r * rec;
             const uint32_t* yz_of_bit[32] = {nullptr};
             uint32_t* U = reinterpret_cast<uint32_t*>(p + 64 * nn);
-            double* L = reinterpret_cast<double*>(p + 64 * nn + 32 * nw);
+            double* L = reinterpret_cast<double*>(p + 64 * nn + u_bytes(nw));
             for (int j = 0; j < per; ++j) {
                 const size_t gi = r * per + j;
                 const HostGroup* g = gi < gs.size() ? gs[gi] : nullptr;
                 const int n = g ? (int)g->c.size() : 0;
                 for (int t = 0; t < n; ++t) yz_of_bit[j * bits + t] = g->yz.data() + (size_t)t * nw;
                 for (int w = 0; w < nw; ++w) U[j * nw + w] = g ? g->u[w] : 0u;
+                if (nw == 1) U[8 + j] = g ? g->u[0] << 3 : 0u;
                 for (unsigned pat = 0; pat < (1u << bits); ++pat) L[j * (1 << bits) + pat] = g ? lut_entry(g->c.data(), n, pat) : 0.0;
             }
             fill_nibble_tables(p, nn, nw, yz_of_bit, per * bits);
@@ -128,29 +136,31 @@ inline void build_sliced_host(const std::vector<HostGroup>& groups, int n_qubits
     S.resize(S.size() + out.n_rec_b * rb, 0);
     pack(gb, out.n_rec_b, rb, 5, 6, out.off_b);
     out.off_c = S.size();
-    // big groups: blobs of at most max_words words
+    // big groups (> 6 terms): consecutive chunks of 6 terms, each with its own 64-entry LUT of serially accumulated signed
+    // sums; 5 chunks (30 terms) share a parity word; blobs of at most max_words words, each blob a self-contained
+    // pseudo-group (same u).  The kernel adds the chunk sums of a blob in order, so H_ij of a big group is the reference's
+    // serial sum re-associated at the chunk / blob boundaries (exact in real arithmetic, within a few ulp in floating
+    // point); the direct formulation keeps the fully serial order.
     const size_t max_words = std::max<size_t>(1, (max_blob_bytes - kBlobHeader) / rc);
     for (const HostGroup* g : gc) {
-        const size_t n = g->c.size(), total_words = (n + 31) / 32;
+        const size_t n = g->c.size(), total_words = (n + 29) / 30;
         for (size_t w0 = 0; w0 < total_words; w0 += max_words) {
             const size_t nwords = std::min(max_words, total_words - w0);
-            const size_t t0 = w0 * 32, t1 = std::min(n, (w0 + nwords) * 32);
             const size_t off = S.size();
             S.resize(off + kBlobHeader + nwords * rc, 0);
             uint32_t* hdr = reinterpret_cast<uint32_t*>(S.data() + off);
             hdr[0] = (uint32_t)nwords;
-            hdr[1] = (uint32_t)((t1 - t0 + 7) / 8);
-            hdr[2] = (w0 == 0 ? kBlobFirst : 0u) | (w0 + nwords >= total_words ? kBlobLast : 0u);
             for (int w = 0; w < nw; ++w) hdr[4 + w] = g->u[w];
             for (size_t q = 0; q < nwords; ++q) {
                 unsigned char* p = S.data() + off + kBlobHeader + q * rc;
                 const uint32_t* yz_of_bit[32] = {nullptr};
-                double* C = reinterpret_cast<double*>(p + 64 * nn);
-                for (int b = 0; b < 32; ++b) {
-                    const size_t t = t0 + q * 32 + b;
-                    if (t < t1) { yz_of_bit[b] = g->yz.data() + t * nw; C[b] = g->c[t]; } else C[b] = 0.0;  // +0.0 padding is exact
+                double* L = reinterpret_cast<double*>(p + 64 * nn);
+                for (int j = 0; j < 5; ++j) {
+                    const size_t t0 = std::min(n, (w0 + q) * 30 + (size_t)j * 6), t1 = std::min(n, t0 + 6);
+                    for (size_t t = t0; t < t1; ++t) yz_of_bit[j * 6 + (t - t0)] = g->yz.data() + t * nw;
+                    for (unsigned pat = 0; pat < 64; ++pat) L[j * 64 + pat] = lut_entry(g->c.data() + t0, (int)(t1 - t0), pat);  // empty chunk: +0.0
                 }
-                fill_nibble_tables(p, nn, nw, yz_of_bit, 32);
+                fill_nibble_tables(p, nn, nw, yz_of_bit, 30);
             }
             out.blobs.push_back({off, kBlobHeader + nwords * rc});
         }
@@ -230,6 +240,33 @@ __device__ __forceinline__ const float2* dense_entry32(const float2* __restrict_
     unsigned long long addr;
     asm("mad.wide.u32 %0, %1, 8, %2;" : "=l"(addr) : "r"(key), "l"(base));
     return reinterpret_cast<const float2*>(addr);
+}
+
+// complex64 direct-address table whose base is aligned to its size (a power of two): the byte address of entry s ^ u is
+// (base ^ s * 8) ^ (u * 8) — ONE LOP3 per group from the per-thread word a0 = low32(base) ^ s * 8 and the pre-shifted flip
+// mask u8 of the record; the high address word is shared.  Sector test on the shifted key with shifted masks (sec8).
+template <bool SEC, int B>
+__device__ __forceinline__ void emit_batch32(const double (&h)[B], const uint32_t (&u8)[B], uint32_t a0, uint32_t base_hi, bool valid,
+                                             const Sector& sec8, double& e_re, double& e_im) {
+    float2 q[B];
+    double hh[B];
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+        const uint32_t lo = a0 ^ u8[b];
+        unsigned long long addr;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(addr) : "r"(lo), "r"(base_hi));
+        q[b] = __ldg(reinterpret_cast<const float2*>(addr));
+        hh[b] = h[b];
+        if constexpr (SEC) {
+            const uint32_t j8[1] = {lo};  // bits above the table size belong to the base and are masked off by sec8
+            hh[b] = ((h[b] != 0.0) & valid && in_sector<1>(j8, sec8)) ? h[b] : 0.0;
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+        e_re = __fma_rn(hh[b], (double)q[b].x, e_re);
+        e_im = __fma_rn(hh[b], (double)q[b].y, e_im);
+    }
 }
 
 // Accumulate H[b] * psi_table(s ^ u_b) for a batch of B groups (dense lookup).  All B table reads are issued before any
@@ -375,7 +412,8 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                    int psi_dtype, int64_t M, double2* __restrict__ out, double2* __restrict__ partial) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t mbar[2];
-    constexpr int REC_A = 64 * NN + 32 * NW + 1024, REC_B = 64 * NN + 32 * NW + 2560, REC_C = 64 * NN + 256;
+    constexpr int UB = NW == 1 ? 64 : 32 * NW;  // u_bytes(NW)
+    constexpr int REC_A = 64 * NN + UB + 1024, REC_B = 64 * NN + UB + 2560, REC_C = 64 * NN + 2560;
 
     const int tile_lo = blockIdx.y * tiles_per_chunk;
     const int tile_hi = min(sv.n_tiles, tile_lo + tiles_per_chunk);
@@ -395,6 +433,11 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
         }
     }
     __syncthreads();
+    // complex64 direct-address table (PSI32): base split into words, sector masks shifted like the keys (see emit_batch32)
+    const uint32_t base_lo = (uint32_t)reinterpret_cast<unsigned long long>(lv.dense32);
+    const uint32_t base_hi = (uint32_t)(reinterpret_cast<unsigned long long>(lv.dense32) >> 32);
+    Sector sec8 = sec;
+    sec8.even[0] <<= 3; sec8.odd[0] <<= 3;
     uint32_t phase0 = 0, phase1 = 0;
     bool have_resident = false;
 
@@ -410,7 +453,7 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
         bool valid = m < M;
         uint32_t s[NW];
         if constexpr (KEYORDER) {
-            s[0] = (uint32_t)m;
+            s[0] = valid ? (uint32_t)m : 0u;  // threads past the key space read entry 0 (table reads are unconditional)
 #pragma unroll
             for (int w = 1; w < NW; ++w) s[w] = 0;
             valid = valid && ((need[m >> 5] >> (m & 31)) & 1u);
@@ -423,8 +466,8 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
         }
         uint32_t nib[NN];
         state_nibbles<NW, NN>(s, nib);
-        double e_re = 0.0, e_im = 0.0, acc = 0.0;
-        uint32_t flip = 0;  // sign currently folded into acc (bit 31): acc holds (-1)^flip * partial sum
+        const uint32_t a0 = base_lo ^ (s[0] << 3);  // PSI32 only
+        double e_re = 0.0, e_im = 0.0;
 
         // hash mode: couplings with H != 0 are parked in a per-thread queue (shared memory, [slot][thread] layout, one
         // 32-bit word each: LUT entry offset | flip-mask offset inside the current tile) and resolved in warp-wide
@@ -457,13 +500,14 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
 
         auto process = [&](const unsigned char* __restrict__ buf, const uint32_t tl_kind, const uint32_t tl_count) {
             if (tl_kind == kSecA) {
-                for (uint32_t r = 0; r < tl_count; ++r) {
-                    const unsigned char* rec = buf + (size_t)r * REC_A;
+                const unsigned char* rec = buf;
+                for (uint32_t r = 0; r < tl_count; ++r, rec += REC_A) {
                     const uint32_t P = parity_word<NN>(rec, nib);
                     const uint32_t* U = reinterpret_cast<const uint32_t*>(rec + 64 * NN);
-                    const unsigned char* L = rec + 64 * NN + 32 * NW;
+                    const unsigned char* L = rec + 64 * NN + UB;
                     if constexpr (LK == kLookDense) {
-                        const uint4 ua = *reinterpret_cast<const uint4*>(U), ub = *reinterpret_cast<const uint4*>(U + 4);
+                        const uint32_t* Ux = PSI32 ? U + 8 : U;  // complex64 table: flip masks as byte offsets (u * 8)
+                        const uint4 ua = *reinterpret_cast<const uint4*>(Ux), ub = *reinterpret_cast<const uint4*>(Ux + 4);
                         const uint32_t uu[2][4] = {{ua.x, ua.y, ua.z, ua.w}, {ub.x, ub.y, ub.z, ub.w}};
 #pragma unroll
                         for (int j0 = 0; j0 < 8; j0 += 4) {
@@ -474,10 +518,10 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                                 const uint32_t off = j == 0 ? ((P << 3) & 0x78u) : ((P >> (4 * j - 3)) & 0x78u);
                                 h[jj] = *reinterpret_cast<const double*>(L + j * 128 + off);
                             }
-                            emit_batch<NW, SEC, KEYORDER, PSI32, 4>(h, uu[j0 / 4], s, valid, sec, lv, e_re, e_im);
+                            if constexpr (PSI32) emit_batch32<SEC, 4>(h, uu[j0 / 4], a0, base_hi, valid, sec8, e_re, e_im);
+                            else emit_batch<NW, SEC, KEYORDER, false, 4>(h, uu[j0 / 4], s, valid, sec, lv, e_re, e_im);
                         }
                     } else {
-#pragma unroll
                         // entry = (LUT entry offset / 8) | (flip-mask offset / 4) << 16, both relative to the tile buffer
                         const uint32_t ebase = ((uint32_t)(L - buf) >> 3) | (((uint32_t)(reinterpret_cast<const unsigned char*>(U) - buf) >> 2) << 16);
 #pragma unroll
@@ -489,23 +533,24 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                     }
                 }
             } else if (tl_kind == kSecB) {
-                for (uint32_t r = 0; r < tl_count; ++r) {
-                    const unsigned char* rec = buf + (size_t)r * REC_B;
+                const unsigned char* rec = buf;
+                for (uint32_t r = 0; r < tl_count; ++r, rec += REC_B) {
                     const uint32_t P = parity_word<NN>(rec, nib);
                     const uint32_t* U = reinterpret_cast<const uint32_t*>(rec + 64 * NN);
-                    const unsigned char* L = rec + 64 * NN + 32 * NW;
+                    const unsigned char* L = rec + 64 * NN + UB;
                     if constexpr (LK == kLookDense) {
-                        const uint4 ua = *reinterpret_cast<const uint4*>(U);
-                        const uint32_t uu[5] = {ua.x, ua.y, ua.z, ua.w, U[4]};
+                        const uint32_t* Ux = PSI32 ? U + 8 : U;
+                        const uint4 ua = *reinterpret_cast<const uint4*>(Ux);
+                        const uint32_t uu[5] = {ua.x, ua.y, ua.z, ua.w, Ux[4]};
                         double h[5];
 #pragma unroll
                         for (int j = 0; j < 5; ++j) {
                             const uint32_t off = j == 0 ? ((P << 3) & 0x1f8u) : ((P >> (6 * j - 3)) & 0x1f8u);
                             h[j] = *reinterpret_cast<const double*>(L + j * 512 + off);
                         }
-                        emit_batch<NW, SEC, KEYORDER, PSI32, 5>(h, uu, s, valid, sec, lv, e_re, e_im);
+                        if constexpr (PSI32) emit_batch32<SEC, 5>(h, uu, a0, base_hi, valid, sec8, e_re, e_im);
+                        else emit_batch<NW, SEC, KEYORDER, false, 5>(h, uu, s, valid, sec, lv, e_re, e_im);
                     } else {
-#pragma unroll
                         const uint32_t ebase = ((uint32_t)(L - buf) >> 3) | (((uint32_t)(reinterpret_cast<const unsigned char*>(U) - buf) >> 2) << 16);
 #pragma unroll
                         for (int j = 0; j < 5; ++j) {
@@ -519,36 +564,28 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                 const unsigned char* p = buf;
                 for (uint32_t b = 0; b < tl_count; ++b) {
                     const uint32_t* hdr = reinterpret_cast<const uint32_t*>(p);
-                    const uint32_t n_words = hdr[0], n_sub8 = hdr[1], flags = hdr[2];
-                    if (flags & kBlobFirst) { acc = 0.0; flip = 0; }
+                    const uint32_t n_words = hdr[0];
+                    double acc = 0.0;  // every blob is self-contained: sum_u-blobs (H_blob * psi(s ^ u)) — tiles of one group may run in different CTAs (table chunks)
                     const unsigned char* rec = p + kBlobHeader;
                     for (uint32_t q = 0; q < n_words; ++q, rec += REC_C) {
                         const uint32_t P = parity_word<NN>(rec, nib);
-                        // acc carries the sign of the previous term; D marks where the sign changes between
-                        // consecutive terms, so each term costs shift + XOR (on acc's high word) + DADD:
-                        //   (-1)^f (x) + c  ==  (-1)^f (x + (-1)^f c)
-                        const uint32_t D = P ^ ((P << 1) | (flip >> 31));
-                        flip = P & 0x80000000u;
-                        const double* C = reinterpret_cast<const double*>(rec + 64 * NN);
-                        const uint32_t nsb = min(4u, n_sub8 - 4u * q);
-                        for (uint32_t sb = 0; sb < nsb; ++sb) {
-                            const uint32_t Db = D >> (8 * sb);
+                        const unsigned char* L = rec + 64 * NN;
 #pragma unroll
-                            for (int t = 0; t < 8; t += 2) {
-                                const double2 cc = *reinterpret_cast<const double2*>(C + sb * 8 + t);  // one LDS.128, two terms
-                                int hi = __double2hiint(acc) ^ (int)((Db << (31 - t)) & 0x80000000u);
-                                acc = __dadd_rn(__hiloint2double(hi, __double2loint(acc)), cc.x);
-                                hi = __double2hiint(acc) ^ (int)((Db << (30 - t)) & 0x80000000u);
-                                acc = __dadd_rn(__hiloint2double(hi, __double2loint(acc)), cc.y);
-                            }
+                        for (int j = 0; j < 5; ++j) {  // chunk sums in term order
+                            const uint32_t off = j == 0 ? ((P << 3) & 0x1f8u) : ((P >> (6 * j - 3)) & 0x1f8u);
+                            acc = __dadd_rn(acc, *reinterpret_cast<const double*>(L + j * 512 + off));
                         }
-                        if (nsb < 4) flip = (P << (8 * (4 - nsb))) & 0x80000000u;  // sign of the last processed term
                     }
-                    if (flags & kBlobLast) {
-                        double h[1] = {__hiloint2double(__double2hiint(acc) ^ (int)flip, __double2loint(acc))};
+                    {
+                        double h[1] = {acc};
                         if constexpr (LK == kLookDense) {
-                            const uint32_t u1[1] = {hdr[4]};
-                            emit_batch<NW, SEC, KEYORDER, PSI32, 1>(h, u1, s, valid, sec, lv, e_re, e_im);
+                            if constexpr (PSI32) {
+                                const uint32_t u1[1] = {hdr[4] << 3};
+                                emit_batch32<SEC, 1>(h, u1, a0, base_hi, valid, sec8, e_re, e_im);
+                            } else {
+                                const uint32_t u1[1] = {hdr[4]};
+                                emit_batch<NW, SEC, KEYORDER, false, 1>(h, u1, s, valid, sec, lv, e_re, e_im);
+                            }
                         }
                         else {
                             const uint32_t* uu[1] = {hdr + 4};

@@ -266,6 +266,8 @@ int naqs_table_create(naqs_table_t** out, const uint64_t* h_xy, const uint64_t* 
         t->nn = sh.nn;
         t->stream_bytes = sh.stream.size();
     }
+    t->coeff_f32_exact = true;
+    for (int64_t k = 0; k < K; ++k) t->coeff_f32_exact = t->coeff_f32_exact && ((double)(float)h_coeff[k] == h_coeff[k] || h_coeff[k] != h_coeff[k]);
     const char* algo_env = getenv("NAQS_ELOC_ALGO");
     t->algo = (algo_env && std::string(algo_env) == "direct") ? 1 : 0;
 
@@ -300,7 +302,7 @@ int naqs_table_destroy(naqs_table_t* t) {
     if (!t) return NAQS_OK;
     DeviceGuard guard(t->device);
     cudaFree(t->d_yz); cudaFree(t->d_coeff); cudaFree(t->d_gxy); cudaFree(t->d_gstart);
-    cudaFree(t->d_dense); cudaFree(t->d_dense32); cudaFree(t->d_slots); cudaFree(t->d_buckets); cudaFree(t->d_filter); cudaFree(t->d_ws); cudaFree(t->d_stage);
+    cudaFree(t->d_dense); cudaFree(t->d_dense32_raw); cudaFree(t->d_slots); cudaFree(t->d_buckets); cudaFree(t->d_filter); cudaFree(t->d_ws); cudaFree(t->d_stage);
     if (t->h_pinned) cudaFreeHost(t->h_pinned);
     if (t->own_stream) cudaStreamDestroy(t->own_stream);
     cudaFree(t->d_tiles); cudaFree(t->d_binom); cudaFree(t->d_stream); cudaFree(t->d_partial);
@@ -346,8 +348,11 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
                            !getenv("NAQS_ELOC_NO_KEYORDER") && !getenv("NAQS_ELOC_NO_DENSE32");
         if (use32) {
             if (t->dense32_entries < entries) {
-                cudaFree(t->d_dense32); t->d_dense32 = nullptr; t->dense32_entries = 0;
-                NAQS_CUDA(cudaMalloc((void**)&t->d_dense32, (size_t)entries * sizeof(float2)));
+                // the kernel forms entry addresses as (base ^ key * 8) ^ (u * 8) (emit_batch32): base aligned to the table size
+                cudaFree(t->d_dense32_raw); t->d_dense32_raw = nullptr; t->d_dense32 = nullptr; t->dense32_entries = 0;
+                const size_t bytes = (size_t)entries * sizeof(float2);
+                NAQS_CUDA(cudaMalloc(&t->d_dense32_raw, 2 * bytes));
+                t->d_dense32 = reinterpret_cast<float2*>(((uintptr_t)t->d_dense32_raw + bytes - 1) & ~(uintptr_t)(bytes - 1));
                 t->dense32_entries = entries;
             }
             NAQS_CUDA(cudaMemsetAsync(t->d_dense32, 0, (size_t)entries * sizeof(float2), stream));
@@ -566,8 +571,18 @@ static int launch_sliced(naqs_table_t* t, const uint64_t* d_states, const void* 
 
 extern "C" {
 
+int naqs_table_set_precision(naqs_table_t* t, int bits) {
+    NAQS_REQUIRE(t && (bits == 32 || bits == 64), NAQS_ERR_DTYPE, "naqs_table_set_precision: bits must be 32 or 64 (long double has no device type)");
+    NAQS_REQUIRE(bits == 64 || t->coeff_f32_exact, NAQS_ERR_ARG,
+                 "naqs_table_set_precision: float32 accumulation needs coefficients already rounded to float32 (couplings.astype(np.float32), hamiltonian.py:424)");
+    t->f32 = bits == 32;
+    if (t->f32) t->algo = 1;  // the sliced LUTs are built from float64 partial sums
+    return NAQS_OK;
+}
+
 int naqs_table_set_algo(naqs_table_t* t, int algo) {
     NAQS_REQUIRE(t && (algo == 0 || algo == 1), NAQS_ERR_ARG, "naqs_table_set_algo: algo must be 0 (sliced) or 1 (direct)");
+    NAQS_REQUIRE(algo == 1 || !t->f32, NAQS_ERR_STATE, "naqs_table_set_algo: a float32 table only has the direct formulation");
     t->algo = algo;
     return NAQS_OK;
 }
@@ -611,6 +626,8 @@ int naqs_lookup_attach_dense32(naqs_table_t* t, const float* d_table, int64_t en
     NAQS_REQUIRE(t->nw32 == 1 && t->n_qubits <= 26 && entries == (1ll << t->n_qubits), NAQS_ERR_ARG,
                  "naqs_lookup_attach_dense32: the table must have exactly 2^n_qubits entries (n_qubits <= 26)");
     NAQS_REQUIRE(t->algo == 0, NAQS_ERR_STATE, "naqs_lookup_attach_dense32: needs the sliced formulation");
+    NAQS_REQUIRE(((uintptr_t)d_table & ((uintptr_t)entries * sizeof(float2) - 1)) == 0, NAQS_ERR_ARG,
+                 "naqs_lookup_attach_dense32: the table must be aligned to its size (8 * 2^n_qubits bytes)");
     t->lookup_kind = NAQS_LOOKUP_DENSE;
     t->lookup_n = entries;
     t->d_dense32_ext = reinterpret_cast<const float2*>(d_table);

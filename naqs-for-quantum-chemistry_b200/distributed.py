@@ -78,16 +78,26 @@ def can_allreduce_table(table, psi):
     return table.n_qubits <= 22 and table.words == 1 and psi.dtype == torch.complex64
 
 
+def aligned_dense_table(table):
+    """[2^N, 2] int32 device buffer whose address is a multiple of its size (naqs_lookup_attach_dense32 requires it: the
+    kernel forms entry addresses with XORs).  A view into a buffer of twice the size; keep it and pass it back as `out`."""
+    n_bytes = (1 << table.n_qubits) * 8
+    raw = torch.empty(2 * n_bytes, dtype=torch.uint8, device=table.device)
+    off = (-raw.data_ptr()) % n_bytes
+    return raw[off:off + n_bytes].view(torch.int32).view(-1, 2)
+
+
 def allreduce_dense_table(table, keys, psi, group=None, out=None):
     """Multi-GPU lookup build for small key spaces WITHOUT gathering the pairs: every rank scatters its own (key, psi) into a
     direct-address complex64 table pre-filled with -0.0f, the tables are all-reduced with MAX on their int32 bit patterns
     (NCCL over NVLink / NVSwitch, in-switch reduction where available), and the result is attached as the lookup table.
     Volume: 8 * 2^N bytes per rank whatever the number of ranks (an all-gather moves 16 * M * world).  Requires psi to be a
-    function of the state (copies of a key on several ranks are identical): the same contract as duplicates_equal."""
+    function of the state (copies of a key on several ranks are identical): the same contract as duplicates_equal.
+    out: a buffer from aligned_dense_table(table) to reuse between calls."""
     from . import _lib
     n_entries = 1 << table.n_qubits
     if out is None:
-        out = torch.empty((n_entries, 2), dtype=torch.int32, device=table.device)
+        out = aligned_dense_table(table)
     out.fill_(INT32_MIN)
     k = keys if keys.dim() == 2 else keys.reshape(-1, 1)
     with torch.cuda.device(table.device):

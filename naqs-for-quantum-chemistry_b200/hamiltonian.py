@@ -72,8 +72,12 @@ class PauliHamiltonianB200:
         self.couplings = c.astype(dtype).reshape(-1, 1)
         self._unique_XY_sites_idx, self._unique2all_XY_sites_idx = np.unique(self.XY_sites_idx, return_inverse=True)
         self._unique_YZ_sites_idx, self._unique2all_YZ_sites_idx = np.unique(self.YZ_sites_idx, return_inverse=True)
-        # the device accumulates in float64 with the coefficients the reference would hold in `dtype`
+        # float64 (experiments/_base.py:234) or float32 (this constructor's default, as in the reference): the device holds
+        # the coefficients the reference would hold in `dtype` and rounds every partial sum of H_ij to it
+        if np.dtype(dtype) not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise TypeError(f"PauliHamiltonian on the device supports dtype float32 / float64, got {np.dtype(dtype)} (no device type).")
         self.table = DeviceTermTable(xy, yz, self.couplings.reshape(-1).astype(np.float64), N, n_alpha, n_beta, device)
+        self.table.set_precision(dtype)
 
         d = self.hilbert.size
         self.H = csr_matrix(([], ([], [])), shape=(d, d), dtype=self.dtype)

@@ -36,6 +36,7 @@ class DeviceTermTable:
         _lib.check(lib.naqs_table_info(self._h, _lib.ptr(info)))
         self.K, self.Kxy, self.Kyz = int(info[0]), int(info[1]), int(info[2])
         self._lookup_built = False
+        self.precision = np.dtype(np.float64)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -53,6 +54,17 @@ class DeviceTermTable:
         (AND/POPC walk).  Both accumulate every H_ij in reference order; they differ only in speed."""
         code = {"sliced": 0, "direct": 1}[algo]
         _lib.check(_lib.load().naqs_table_set_algo(self._h, code), "naqs_table_set_algo")
+        return self
+
+    def set_precision(self, dtype):
+        """Accumulation type of H_ij: np.float64 (default; what the reference's experiments use, _base.py:234) or np.float32
+        (the constructor default of PauliHamiltonian.get, hamiltonian.py:48): coefficients must already be float32 values and
+        every partial sum is rounded to float32 like __inner_int64_float does, so H_ij equals the reference's float32 matrix
+        bit for bit.  Any other type (np.float128) -> TypeError: it has no device type."""
+        dt = np.dtype(dtype)
+        bits = {np.dtype(np.float64): 64, np.dtype(np.float32): 32}.get(dt, dt.itemsize * 8 if dt.kind == "f" else 0)
+        _lib.check(_lib.load().naqs_table_set_precision(self._h, bits), "naqs_table_set_precision")
+        self.precision = np.dtype(np.float32 if bits == 32 else np.float64)
         return self
 
     # ------------------------------------------------------------------ helpers

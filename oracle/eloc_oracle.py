@@ -245,11 +245,13 @@ def restricted_index(keys, n_qubits, n_alpha, n_beta):
 class TermTable:
     """Packed Pauli sum + the np.unique groupings the reference keeps (hamiltonian.py:241-252)."""
 
-    def __init__(self, xy, yz, coeff, n_qubits, n_alpha=None, n_beta=None):
+    def __init__(self, xy, yz, coeff, n_qubits, n_alpha=None, n_beta=None, dtype=np.float64):
+        """dtype: the reference's `dtype` argument (hamiltonian.py:48,424): couplings are cast to it and H_ij is
+        accumulated in it (float64 in the experiments, _base.py:234; float32 is the constructor default)."""
         self.n_qubits, self.n_alpha, self.n_beta = n_qubits, n_alpha, n_beta
         self.W = n_words(n_qubits)
         self.xy, self.yz = as_keys(xy, self.W), as_keys(yz, self.W)
-        self.coeff = np.asarray(coeff, np.float64).reshape(-1)
+        self.coeff = np.asarray(coeff).reshape(-1).astype(dtype)
         self.unique_xy, self.unique2all_xy = group_terms(self.xy)
         self.unique_yz, self.unique2all_yz = group_terms(self.yz)
 
@@ -311,20 +313,22 @@ def local_energy(table, states, psi, table_keys=None, table_psi=None):
     Summation order over the coupled states of a row: ascending restricted index
     (canonical CSR of hamiltonian.py:350,363 + row-order-preserving sub-matrix :94)."""
     s = as_keys(states, table.W)
-    psi = np.asarray(psi).astype(np.complex128)
+    # __type_mv (sparse_math.pyx:13-41): float32 matrix x complex64 vector stays complex64, everything else is complex128
+    cdt = np.complex64 if (table.coeff.dtype == np.float32 and np.asarray(psi).dtype == np.complex64) else np.complex128
+    psi = np.asarray(psi).astype(cdt)
     tk = s if table_keys is None else as_keys(table_keys, table.W)
-    tp = psi if table_psi is None else np.asarray(table_psi).astype(np.complex128)
+    tp = psi if table_psi is None else np.asarray(table_psi).astype(cdt)
     lut = {}
     for i, v in enumerate(keys_to_int(tk)):
         lut.setdefault(v, []).append(i)
     indptr, cols, vals = hamiltonian_rows(table, s)
     cols_int = keys_to_int(cols) if len(cols) else []
     ridx = restricted_index(cols, table.n_qubits, table.n_alpha, table.n_beta) if len(cols) else np.zeros(0, np.int64)
-    out = np.zeros(len(s), np.complex128)
+    out = np.zeros(len(s), cdt)
     for m in range(len(s)):
         lo, hi = indptr[m], indptr[m + 1]
         order = lo + np.argsort(ridx[lo:hi], kind="stable")
-        acc = 0j
+        acc = cdt(0)
         for e in order:
             for t in lut.get(cols_int[e], ()):
                 acc = acc + vals[e] * tp[t]

@@ -14,7 +14,9 @@ Files:
                           (hamiltonian.py:373-430) + the np.unique group counts (:248-249)
   known_answers.json      full-sector H fingerprints: nnz, trace, sum|H|, E0
   eloc_<case>.npz         seeded batches: states, psi (complex64), eloc (complex128) from
-                          energy.py:245-248; for small cases also the stored CSR rows of H
+                          energy.py:245-248; for small cases also the stored CSR rows of H.
+                          *_f32 cases: the same with PauliHamiltonian.get(dtype=np.float32), the constructor
+                          default (float32 H_ij, E_loc computed by the reference in complex64); h_bits = 32
   level0.npz              input/output pairs of the five Cython entry points
   terms_<mol>.json        the raw Pauli strings of H2 / LiH (inputs for the pack_terms tests; the pickles cannot travel)
 """
@@ -85,9 +87,16 @@ def _psi(n, seed):
     return (rng.normal(size=n) + 1j * rng.normal(size=n)).astype(np.complex64)
 
 
-def make_eloc():
+F32_CASES = [  # the constructor-default dtype=np.float32 (hamiltonian.py:48): float32 H_ij, complex64 E_loc
+    ("LiH_sector_f32", "LiH", True, None, 21, True, np.float32),
+    ("H2O_300_f32", "H2O", True, 300, 22, True, np.float32),
+    ("N2_full_1000_f32", "N2", False, 1000, 23, False, np.float32),
+]
+
+
+def make_eloc(cases=None):
     mods = rh.reference_modules()
-    cases = [  # name, molecule, restricted, batch size (None = sector minus one, avoids quirk q1), seed, with_rows
+    cases = cases or [  # name, molecule, restricted, batch size (None = sector minus one, avoids quirk q1), seed, with_rows
         ("LiH_sector", "LiH", True, None, 11, True),
         ("LiH_small", "LiH", True, 50, 12, True),
         ("H2O_sector", "H2O", True, None, 13, True),
@@ -97,8 +106,9 @@ def make_eloc():
         ("N2_full_3000", "N2", False, 3000, 17, False),
         ("LiH_full_600", "LiH", False, 600, 18, True),
     ]
-    for name, mol, restricted, m, seed, with_rows in cases:
-        hil, ph = rh.make_reference(mol, restricted=restricted)
+    for name, mol, restricted, m, seed, with_rows, *rest in cases:
+        h_dtype = rest[0] if rest else np.float64
+        hil, ph = rh.make_reference(mol, restricted=restricted, dtype=h_dtype)
         rng = np.random.default_rng(seed)
         if restricted:
             sec = hil.get_subspace(ret_states=False, ret_idxs=True).numpy()
@@ -108,7 +118,9 @@ def make_eloc():
             st = rng.choice(2 ** hil.N, m, replace=False).astype(hil._idx_np_dtype)
         psi = _psi(len(st), seed + 100)
         eloc = rh.reference_local_energy(ph, st, psi)
+        assert eloc.dtype == (np.complex64 if h_dtype is np.float32 else np.complex128), eloc.dtype
         d = dict(states=st.astype(np.int64).astype(np.uint64), psi=psi, eloc=eloc.astype(np.complex128),
+                 h_bits=np.array(np.dtype(h_dtype).itemsize * 8, np.int64),
                  meta=np.array([hil.N, rh.MOLECULES[mol][1] if restricted else -1, rh.MOLECULES[mol][2] if restricted else -1], np.int64))
         if with_rows:
             H = ph.get_H()
@@ -120,7 +132,8 @@ def make_eloc():
             d["rows_cols_restricted"] = cols
             d["rows_cols_keys"] = (np.asarray(hil.restricted2full_idx(cols)).astype(np.int64).astype(np.uint64)
                                    if restricted else cols.astype(np.uint64))
-            d["rows_vals"] = np.concatenate(vals).astype(np.float64)
+            assert H.dtype == np.dtype(h_dtype), H.dtype
+            d["rows_vals"] = np.concatenate(vals).astype(np.float64)   # float32 values are exact in float64
             d["coupled_unique_restricted"] = np.asarray(ph.get_coupled_state_idxs(ridx, return_unique=True)).astype(np.int64)
         np.savez_compressed(os.path.join(OUT, f"eloc_{name}.npz"), **d)
         print("eloc", name, len(st), "E[0]=", eloc[0])
@@ -188,5 +201,7 @@ if __name__ == "__main__":
         make_known_answers()
     if "eloc" in which:
         make_eloc()
+    if "eloc" in which or "eloc_f32" in which:
+        make_eloc(F32_CASES)
     if "level0" in which:
         make_level0()

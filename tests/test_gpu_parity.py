@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 import torch
-from conftest import CASE_TABLE, GOLDEN, case_sector, load_case, load_table, random_sector_states
+from conftest import CASE_TABLE, F32_CASE_TABLE, GOLDEN, case_sector, load_case, load_table, random_sector_states
 
 pytestmark = pytest.mark.gpu
 
@@ -105,6 +105,46 @@ def test_rows_match_reference_csr_bit_exact(name):
     assert np.array_equal(np.sort(t.restricted_index(uniq.view(np.int64)).cpu().numpy()), case["coupled_unique_restricted"])
 
 
+@pytest.mark.parametrize("name", sorted(F32_CASE_TABLE))
+def test_float32_hamiltonian_matches_reference_fixture(name):
+    """PauliHamiltonian.get(dtype=np.float32) — the reference constructor's default (hamiltonian.py:48): matrix elements
+    accumulate in float32 (__inner_int64_float) and must be bit-identical; the reference then forms E_loc in complex64
+    (sparse_math.pyx:13-41), the device in complex128, so E_loc agrees to float32 rounding."""
+    nb200, _, eo = _mods()
+    case = load_case(name)
+    xy, yz, c, N, _, _ = load_table(F32_CASE_TABLE[name])
+    na, nb = case_sector(case, name)
+    with pytest.raises(ValueError):  # float64 coefficients are not float32 values
+        nb200.DeviceTermTable(xy, yz, c, N, na, nb).set_precision(np.float32)
+    with pytest.raises(TypeError):   # np.float128 has no device type (hamiltonian_math.pyx long double kernels)
+        nb200.DeviceTermTable(xy, yz, c, N, na, nb).set_precision(np.longdouble)
+    c32 = c.astype(np.float32)
+    t = nb200.DeviceTermTable(xy, yz, c32, N, na, nb).set_precision(np.float32)
+    with pytest.raises(nb200.NaqsError):
+        t.set_algo("sliced")
+    if "rows_vals" in case:
+        indptr, cols, ridx, vals = (x.cpu().numpy() for x in t.rows(case["states"]))
+        assert np.array_equal(indptr, case["rows_indptr"])
+        for m in range(len(indptr) - 1):
+            lo, hi = indptr[m], indptr[m + 1]
+            o = np.argsort(ridx[lo:hi], kind="stable")
+            assert np.array_equal(cols[lo:hi, 0][o].view(np.uint64), case["rows_cols_keys"][lo:hi])
+            assert np.array_equal(vals[lo:hi][o], case["rows_vals"][lo:hi])  # bit-exact float32 matrix elements
+    # dense [M, Kxy] elements against the float32 oracle (itself pinned on the fixture by the CPU suite)
+    H_o, _ = eo.hamiltonian_dense_rows(eo.TermTable(xy, yz, c, N, na, nb, dtype=np.float32), case["states"][:200])
+    assert np.array_equal(t.hij_dense(case["states"][:200]).cpu().numpy(), H_o.astype(np.float64))
+    scale = np.abs(case["eloc"]).max()
+    for kw in ({}, {"kind": nb200._lib.LOOKUP_HASH}, {"assume_unique": True}):
+        e = gpu_eloc(t, case["states"], case["psi"], **kw)
+        assert np.abs(e - case["eloc"]).max() <= 2e-5 * scale
+    # switching back restores float64 accumulation of the same (float32-valued) coefficients
+    t.set_precision(np.float64).set_algo("sliced")
+    e64 = gpu_eloc(t, case["states"], case["psi"])
+    o64 = eo.local_energy(eo.TermTable(xy, yz, c32.astype(np.float64), N, na, nb), case["states"][:100], case["psi"][:100],
+                          table_keys=case["states"], table_psi=case["psi"])
+    assert rel_err(e64[:100], o64).max() <= ELOC_RTOL
+
+
 @pytest.mark.parametrize("mol,sector,m", [("LiH", True, 225), ("N2", True, 6000), ("N2", False, 50000), ("Li2O", True, 4000), ("H2S", True, 2000)])
 def test_direct_and_sliced_formulations_agree(mol, sector, m):
     """The two kernel formulations (AND/POPC walk vs nibble-sliced parity + group LUT) produce the same E_loc; both are
@@ -124,8 +164,10 @@ def test_direct_and_sliced_formulations_agree(mol, sector, m):
             e = gpu_eloc(t, st, psi, kind=kind)
             assert rel_err(e, ref).max() <= ELOC_RTOL, (algo, kind)
             out[(algo, kind)] = e
+    # the sliced formulation adds the 6-term chunk sums of groups with more than 6 terms (sliced.cuh), the direct one walks
+    # every term serially: matrix elements of those groups agree to a few ulp, E_loc well inside the 1e-12 bar
     a, b = out[("sliced", nb200._lib.LOOKUP_HASH)], out[("direct", nb200._lib.LOOKUP_HASH)]
-    assert rel_err(a, b).max() <= 1e-13
+    assert rel_err(a, b).max() <= ELOC_RTOL
 
 
 # ------------------------------------------------------------------------------------------- oracle, seeded
@@ -395,6 +437,20 @@ def test_pauli_hamiltonian_from_pauli_strings_and_calculate_local_energy():
     got_vals = np.concatenate([H.data[H.indptr[i]:H.indptr[i + 1]] for i in r])
     assert np.array_equal(got_cols, case["rows_cols_restricted"]) and np.array_equal(got_vals, case["rows_vals"])
     assert np.array_equal(np.asarray(ph.get_coupled_state_idxs(r, return_unique=True)), case["coupled_unique_restricted"])
+    # the constructor default dtype=np.float32 (hamiltonian.py:48): float32 CSR, bit-identical to the reference's
+    case32 = load_case("LiH_sector_f32")
+    ph32 = nb200.PauliHamiltonian.get(hil, op, restricted_idxs=sec)
+    assert ph32.dtype is np.float32 and ph32.couplings.dtype == np.float32
+    idx32 = case32["states"].astype(np.int64).astype(np.int16)
+    H32 = ph32.update_H(idx32, check_unseen=True, assume_unique=True)
+    assert H32.dtype == np.float32
+    r32 = np.asarray(hil.full2restricted_idx(idx32)).astype(np.int64)
+    got32 = np.concatenate([H32.data[H32.indptr[i]:H32.indptr[i + 1]] for i in r32])
+    assert np.array_equal(got32.astype(np.float64), case32["rows_vals"])
+    e = ph32.local_energy(idx32, case32["psi"])
+    assert np.abs(e - case32["eloc"]).max() <= 2e-5 * np.abs(case32["eloc"]).max()
+    with pytest.raises(TypeError):
+        nb200.PauliHamiltonian.get(hil, op, restricted_idxs=sec, dtype=np.longdouble)
 
 
 # ------------------------------------------------------------------------------------------- full-size properties

@@ -5,7 +5,7 @@ import os
 
 import numpy as np
 import pytest
-from conftest import CASE_TABLE, GOLDEN, case_sector, load_case, load_table, load_terms_json
+from conftest import CASE_TABLE, F32_CASE_TABLE, GOLDEN, case_sector, load_case, load_table, load_terms_json
 
 from oracle import c_oracle
 from oracle import eloc_oracle as eo
@@ -72,6 +72,30 @@ def test_rows_match_reference_csr(name):
         assert np.array_equal(i2, indptr) and np.array_equal(c2, cols) and np.array_equal(v2, vals)
     uniq = np.unique(ridx)
     assert np.array_equal(uniq, case["coupled_unique_restricted"])
+
+
+@pytest.mark.parametrize("name", sorted(F32_CASE_TABLE))
+def test_float32_hamiltonian_oracle(name):
+    """dtype=np.float32 (hamiltonian.py:48 default): float32 couplings, float32 accumulation of H_ij
+    (__inner_int64_float), complex64 mat-vec (sparse_math.pyx:13-41)."""
+    case = load_case(name)
+    assert int(case["h_bits"]) == 32
+    xy, yz, c, N, _, _ = load_table(F32_CASE_TABLE[name])
+    na, nb = case_sector(case, name)
+    t = eo.TermTable(xy, yz, c, N, na, nb, dtype=np.float32)
+    if "rows_vals" in case:
+        indptr, cols, vals = eo.hamiltonian_rows(t, case["states"])
+        assert vals.dtype == np.float32 and np.array_equal(indptr, case["rows_indptr"])
+        ridx = eo.restricted_index(cols, N, na, nb)
+        for m in range(len(indptr) - 1):
+            lo, hi = indptr[m], indptr[m + 1]
+            o = np.argsort(ridx[lo:hi], kind="stable")
+            assert np.array_equal(cols[lo:hi, 0][o], case["rows_cols_keys"][lo:hi])
+            assert np.array_equal(vals[lo:hi][o].astype(np.float64), case["rows_vals"][lo:hi])  # bit-exact float32 elements
+    e = eo.local_energy(t, case["states"], case["psi"])
+    assert e.dtype == np.complex64
+    scale = np.abs(case["eloc"]).max()
+    assert np.abs(e - case["eloc"]).max() <= 2e-5 * scale  # complex64 sums; the order of the adds is the reference's
 
 
 @pytest.mark.parametrize("mol", ["H2", "LiH", "H2O", "NH3", "N2", "C2"])
