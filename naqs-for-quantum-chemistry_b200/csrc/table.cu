@@ -26,6 +26,22 @@ int ensure_ws(naqs_table* t, size_t bytes) {
 }
 
 // ------------------------------------------------------------------------------------------ lookup build
+// Only keys INSIDE the sector enter a lookup structure: a coupled state s ^ u outside the sector can then never be found,
+// which IS the reference's sector filter on coupled states (hamiltonian.py:321-328) — applied once per table key here
+// instead of once per (state, group) pair in the fused kernel.  (Sampled states are in-sector by contract; a stray one
+// is ignored exactly as the reference ignores it.)
+__device__ __forceinline__ bool key_in_sector(const uint64_t* __restrict__ key, int words, const Sector& sec) {
+    if (!sec.enabled) return true;
+    int na = 0, nb = 0;
+    for (int w = 0; w < words; ++w) {
+        const unsigned long long ev = (unsigned long long)sec.even[2 * w] | ((unsigned long long)sec.even[2 * w + 1] << 32);
+        const unsigned long long od = (unsigned long long)sec.odd[2 * w] | ((unsigned long long)sec.odd[2 * w + 1] << 32);
+        na += __popcll(key[w] & ev);
+        nb += __popcll(key[w] & od);
+    }
+    return na == sec.n_alpha && nb == sec.n_beta;
+}
+
 __global__ void hash_init_kernel(HashSlot* slots, int64_t cap) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < cap) {
@@ -47,9 +63,9 @@ __device__ __forceinline__ ulonglong2 cas128(unsigned long long* addr, ulonglong
 }
 
 __global__ void hash_insert_kernel(HashSlot* slots, unsigned long long mask, int shift, const uint64_t* __restrict__ keys, int words,
-                                   const void* __restrict__ psi, int psi_dtype, int64_t n) {
+                                   const void* __restrict__ psi, int psi_dtype, int64_t n, Sector sec) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n || !key_in_sector(keys + i * words, words, sec)) return;
     const unsigned long long k0 = keys[i * words], k1 = words > 1 ? keys[i * words + 1] : 0ull;
     const double2 p = load_psi(psi, psi_dtype, i);
     unsigned long long h = hash_slot(k0, k1, shift);
@@ -74,9 +90,9 @@ __global__ void bucket_init_kernel(HashBucket* buckets, int64_t n) {
 }
 
 __global__ void bucket_insert_kernel(HashBucket* buckets, unsigned bmask, int bshift, const uint64_t* __restrict__ keys, int words,
-                                     const void* __restrict__ psi, int psi_dtype, int64_t n, int keep_one) {
+                                     const void* __restrict__ psi, int psi_dtype, int64_t n, int keep_one, Sector sec) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n || !key_in_sector(keys + i * words, words, sec)) return;
     const unsigned long long k = keys[i * words];
     const double2 p = load_psi(psi, psi_dtype, i);
     unsigned b = hash32(k, 0ull) >> bshift;
@@ -100,9 +116,9 @@ __global__ void bucket_insert_kernel(HashBucket* buckets, unsigned bmask, int bs
     }
 }
 
-__global__ void filter_build_kernel(uint32_t* filter, const uint64_t* __restrict__ keys, int words, int64_t n) {
+__global__ void filter_build_kernel(uint32_t* filter, const uint64_t* __restrict__ keys, int words, int64_t n, Sector sec) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n || !key_in_sector(keys + i * words, words, sec)) return;
     uint32_t b1, b2;
     filter_positions(keys[i * words], hash32(keys[i * words], 0ull), b1, b2);
     atomicOr(&filter[b1 >> 5], 1u << (b1 & 31));
@@ -120,15 +136,15 @@ __global__ void narrow_eloc_kernel(const double2* __restrict__ in, int64_t n, fl
     if (i < n) out[i] = make_float2((float)in[i].x, (float)in[i].y);
 }
 
-__global__ void dense_scatter32_kernel(float2* dense, const uint64_t* __restrict__ keys, const float2* __restrict__ psi, int64_t n) {
+__global__ void dense_scatter32_kernel(float2* dense, const uint64_t* __restrict__ keys, const float2* __restrict__ psi, int64_t n, Sector sec) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dense[keys[i]] = psi[i];  // unique keys (caller's guarantee): a plain store
+    if (i < n && key_in_sector(keys + i, 1, sec)) dense[keys[i]] = psi[i];  // unique keys (caller's guarantee): a plain store
 }
 
 __global__ void dense_scatter_kernel(double2* dense, const uint64_t* __restrict__ keys, const void* __restrict__ psi,
-                                     int psi_dtype, int64_t n, int overwrite) {
+                                     int psi_dtype, int64_t n, int overwrite, Sector sec) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n || !key_in_sector(keys + i, 1, sec)) return;
     const double2 p = load_psi(psi, psi_dtype, i);
     if (overwrite) { dense[keys[i]] = p; return; }  // copies of a key carry the same amplitude: keep one
     double* dst = reinterpret_cast<double*>(dense + keys[i]);
@@ -357,14 +373,14 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
             }
             NAQS_CUDA(cudaMemsetAsync(t->d_dense32, 0, (size_t)entries * sizeof(float2), stream));
             if (n > 0) {
-                dense_scatter32_kernel<<<blocks, 256, 0, stream>>>(t->d_dense32, d_keys, reinterpret_cast<const float2*>(d_psi), n);
+                dense_scatter32_kernel<<<blocks, 256, 0, stream>>>(t->d_dense32, d_keys, reinterpret_cast<const float2*>(d_psi), n, t->sector);
                 NAQS_LAUNCHED();
             }
             t->dense32_valid = true;
         } else {
             NAQS_CUDA(cudaMemsetAsync(t->d_dense, 0, (size_t)entries * sizeof(double2), stream));
             if (n > 0) {
-                dense_scatter_kernel<<<blocks, 256, 0, stream>>>(t->d_dense, d_keys, d_psi, psi_dtype, n, dup_equal ? 1 : 0);
+                dense_scatter_kernel<<<blocks, 256, 0, stream>>>(t->d_dense, d_keys, d_psi, psi_dtype, n, dup_equal ? 1 : 0, t->sector);
                 NAQS_LAUNCHED();
             }
         }
@@ -384,14 +400,14 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
         NAQS_LAUNCHED();
         if (n > 0) {
             const LookupView lv = t->lookup();
-            bucket_insert_kernel<<<blocks, 256, 0, stream>>>(t->d_buckets, lv.bmask, lv.bshift, d_keys, t->words, d_psi, psi_dtype, n, dup_equal ? 1 : 0);
+            bucket_insert_kernel<<<blocks, 256, 0, stream>>>(t->d_buckets, lv.bmask, lv.bshift, d_keys, t->words, d_psi, psi_dtype, n, dup_equal ? 1 : 0, t->sector);
             NAQS_LAUNCHED();
         }
         t->filter_valid = false;
         if (n > 0 && n * 4 <= (int64_t)kFilterBits && !getenv("NAQS_ELOC_NO_FILTER")) {
             if (!t->d_filter) NAQS_CUDA(cudaMalloc((void**)&t->d_filter, kFilterBytes));
             NAQS_CUDA(cudaMemsetAsync(t->d_filter, 0, kFilterBytes, stream));
-            filter_build_kernel<<<blocks, 256, 0, stream>>>(t->d_filter, d_keys, t->words, n);
+            filter_build_kernel<<<blocks, 256, 0, stream>>>(t->d_filter, d_keys, t->words, n, t->sector);
             NAQS_LAUNCHED();
             t->filter_valid = true;
         }
@@ -411,7 +427,7 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
         NAQS_LAUNCHED();
         if (n > 0) {
             hash_insert_kernel<<<blocks, 256, 0, stream>>>(t->d_slots, (unsigned long long)(cap - 1), t->lookup().shift, d_keys, t->words,
-                                                           d_psi, psi_dtype, n);
+                                                           d_psi, psi_dtype, n, t->sector);
             NAQS_LAUNCHED();
         }
     }
@@ -529,42 +545,36 @@ static int launch_sliced(naqs_table_t* t, const uint64_t* d_states, const void* 
         if (eff_best > best_eff + 1e-9) { best_eff = eff_best; cfg = c; n_chunks = ch_best; }
         if (eff_best >= 0.85) { cfg = c; n_chunks = ch_best; break; }
     }
-    const bool hash = t->lookup_kind == NAQS_LOOKUP_HASH, secf = t->sector.enabled != 0;
+    // lookup structures built by this library hold in-sector keys only (key_in_sector above), so a coupled state outside the
+    // sector simply misses: the kernel needs its own sector test only for a caller-owned table (naqs_lookup_attach_dense32)
+    const bool hash = t->lookup_kind == NAQS_LOOKUP_HASH;
+    const bool secf = t->sector.enabled != 0 && t->dense32_valid && t->d_dense32_ext != nullptr;
     if constexpr (NW == 1) {
         if (keyorder) {
 #define NAQS_KO(CFG, SEC, P32) launch_sliced_cfg<NW, NN, CFG, kLookDense, SEC, true, P32>(t, d_states, d_psi, psi_dtype, M_rows, d_eloc, stream, n_chunks, sm_count)
             switch (cfg * 4 + (secf ? 2 : 0) + (t->dense32_valid ? 1 : 0)) {
                 case 0: return NAQS_KO(0, false, false);
                 case 1: return NAQS_KO(0, false, true);
-                case 2: return NAQS_KO(0, true, false);
                 case 3: return NAQS_KO(0, true, true);
                 case 4: return NAQS_KO(1, false, false);
                 case 5: return NAQS_KO(1, false, true);
-                case 6: return NAQS_KO(1, true, false);
                 case 7: return NAQS_KO(1, true, true);
                 case 8: return NAQS_KO(2, false, false);
                 case 9: return NAQS_KO(2, false, true);
-                case 10: return NAQS_KO(2, true, false);
                 default: return NAQS_KO(2, true, true);
             }
 #undef NAQS_KO
         }
     }
     if (NW > 1 && !hash) { set_error("naqs_eloc: dense lookup needs n_qubits <= 30"); return NAQS_ERR_STATE; }
-#define NAQS_SL(CFG, LK, SEC) launch_sliced_cfg<NW, NN, CFG, (NW > 1 ? kLookHash : LK), SEC, false>(t, d_states, d_psi, psi_dtype, M, d_eloc, stream, n_chunks, sm_count)
-    switch (cfg * 4 + (hash ? 2 : 0) + (secf ? 1 : 0)) {
-        case 0: return NAQS_SL(0, kLookDense, false);
-        case 1: return NAQS_SL(0, kLookDense, true);
-        case 2: return NAQS_SL(0, kLookHash, false);
-        case 3: return NAQS_SL(0, kLookHash, true);
-        case 4: return NAQS_SL(1, kLookDense, false);
-        case 5: return NAQS_SL(1, kLookDense, true);
-        case 6: return NAQS_SL(1, kLookHash, false);
-        case 7: return NAQS_SL(1, kLookHash, true);
-        case 8: return NAQS_SL(2, kLookDense, false);
-        case 9: return NAQS_SL(2, kLookDense, true);
-        case 10: return NAQS_SL(2, kLookHash, false);
-        default: return NAQS_SL(2, kLookHash, true);
+#define NAQS_SL(CFG, LK) launch_sliced_cfg<NW, NN, CFG, (NW > 1 ? kLookHash : LK), false, false>(t, d_states, d_psi, psi_dtype, M, d_eloc, stream, n_chunks, sm_count)
+    switch (cfg * 2 + (hash ? 1 : 0)) {
+        case 0: return NAQS_SL(0, kLookDense);
+        case 1: return NAQS_SL(0, kLookHash);
+        case 2: return NAQS_SL(1, kLookDense);
+        case 3: return NAQS_SL(1, kLookHash);
+        case 4: return NAQS_SL(2, kLookDense);
+        default: return NAQS_SL(2, kLookHash);
     }
 #undef NAQS_SL
 }
@@ -615,8 +625,10 @@ int naqs_eloc(naqs_table_t* t, const uint64_t* d_states, const void* d_psi, int 
 int naqs_dense32_scatter(float* d_table, const uint64_t* d_keys, const void* d_psi, int64_t n, void* stream) {
     NAQS_REQUIRE(n >= 0 && (n == 0 || (d_table && d_keys && d_psi)), NAQS_ERR_ARG, "naqs_dense32_scatter: NULL buffers");
     if (n == 0) return NAQS_OK;
+    Sector none;  // no table handle here: the fused kernel keeps its own sector test for caller-owned tables
+    std::memset(&none, 0, sizeof(none));
     dense_scatter32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2*>(d_table), d_keys,
-                                                                                        reinterpret_cast<const float2*>(d_psi), n);
+                                                                                        reinterpret_cast<const float2*>(d_psi), n, none);
     NAQS_LAUNCHED();
     return NAQS_OK;
 }
