@@ -318,6 +318,22 @@ __device__ __forceinline__ void emit_batch(const double (&h)[B], const uint32_t 
     }
 }
 
+// Stage 1 of the two-stage hash lookup (launch shape with the shared-memory Bloom filter): is the coupled state s ^ u
+// possibly in the table?  A clear filter bit proves it is not — ~90 % of the couplings of a large-sector batch end here
+// without touching global memory.
+template <int NW>
+__device__ __forceinline__ bool filter_pass(const uint32_t* __restrict__ u, const uint32_t (&s)[NW], const uint32_t* __restrict__ sfilt) {
+    static_assert(NW <= 2, "the Bloom filter accompanies the bucketed table (keys <= 63 bits)");
+    uint32_t j[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) j[w] = s[w] ^ u[w];
+    unsigned long long k0, k1;
+    key_words64<NW>(j, k0, k1);
+    uint32_t b1, b2;
+    filter_positions(k0, hash32(k0, 0ull), b1, b2);
+    return ((sfilt[b1 >> 5] >> (b1 & 31)) & (sfilt[b2 >> 5] >> (b2 & 31)) & 1u) != 0;
+}
+
 // Hash-lookup ("heavy") epilogue of up to B couplings of one thread: sector filter (hamiltonian.py:328), shared-memory
 // Bloom filter when the launch shape carries one, probe of the bucketed table (keys <= 63 bits: one 256-bit load reads
 // the four keys of a 128-byte bucket) or of the 32-byte-slot table (wider keys), complex multiply-add.  Called only for couplings whose H is not exactly 0.0
@@ -396,6 +412,7 @@ __device__ __forceinline__ void heavy_lookup(int n, const double (&h)[B], const 
 }
 
 constexpr int kQueueCap = 16;  // pending couplings per thread (hash mode)
+constexpr int kQueue2Cap = 6;  // couplings per thread that passed the Bloom filter and await their table probe (filter shape only)
 
 // One state per thread.  Each CTA owns state blocks blockIdx.x, blockIdx.x + gridDim.x, ... and walks the
 // tiles [tile_lo, tile_hi) of its chunk (blockIdx.y) for each of them; with a single tile the table stays
@@ -477,20 +494,59 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
         unsigned char* const q0 = smem + queue_offset + threadIdx.x * 4;
         unsigned char* qtail = q0;            // the queue holds (qtail - q0) / QSTRIDE couplings
         constexpr int PB = 2;  // couplings resolved per thread and round
-        auto pop_round = [&](const unsigned char* __restrict__ buf) {
-            const int n = min((int)((uint32_t)(qtail - q0) / QSTRIDE), PB);
+        // Two stages when the Bloom filter is present.  Stage 1 (filter_round) pops couplings, tests the filter in shared
+        // memory and moves the ~10 % survivors to a second per-thread queue; stage 2 (probe_round) runs once some lane
+        // holds >= 4 survivors and does the global bucket probes with many lanes busy — a round that waits on L2 for two
+        // lanes out of 32 was the largest stall of the one-stage version.  Without a filter a single stage does it all.
+        unsigned char* const q2end = smem + filter_offset + kFilterBytes + (size_t)kQueue2Cap * QSTRIDE + threadIdx.x * 4;
+        unsigned char* q2 = q2end;            // survivors occupy [q2, q2end), growing downwards
+        auto pop_entries = [&](unsigned char* base, int n, bool down, uint32_t (&e)[PB]) {
+#pragma unroll
+            for (int b = 0; b < PB; ++b) {
+                // always read a valid slot (an arbitrary one of the queue when it is shorter than b + 1): no branch, lanes are masked by n
+                const unsigned char* slot = down ? (b < n ? base - (b + 1) * QSTRIDE : q0) : (b < n ? base + b * QSTRIDE : q0);
+                e[b] = *reinterpret_cast<const uint32_t*>(slot);
+            }
+        };
+        auto resolve = [&](const unsigned char* __restrict__ buf, int n, const uint32_t (&e)[PB], const uint32_t* filt) {
             double h[PB];
             const uint32_t* u[PB];
 #pragma unroll
             for (int b = 0; b < PB; ++b) {
-                // always read a valid slot (the oldest one when the queue is shorter than b + 1): no branch, lanes are masked by n
-                const unsigned char* slot = b < n ? qtail - (b + 1) * QSTRIDE : q0;
-                const uint32_t e = *reinterpret_cast<const uint32_t*>(slot);
-                h[b] = *reinterpret_cast<const double*>(buf + (e & 0xffffu) * 8u);
-                u[b] = reinterpret_cast<const uint32_t*>(buf + (e >> 16) * 4u);
+                h[b] = *reinterpret_cast<const double*>(buf + (e[b] & 0xffffu) * 8u);
+                u[b] = reinterpret_cast<const uint32_t*>(buf + (e[b] >> 16) * 4u);
             }
+            heavy_lookup<NW, SEC, PB>(n, h, u, s, sec, lv, filt, e_re, e_im);
+        };
+        auto probe_round = [&](const unsigned char* __restrict__ buf) {
+            const int n = min((int)((uint32_t)(q2end - q2) / QSTRIDE), PB);
+            uint32_t e[PB];
+            pop_entries(q2, n, false, e);
+            q2 += n * QSTRIDE;
+            resolve(buf, n, e, nullptr);
+        };
+        auto pop_round = [&](const unsigned char* __restrict__ buf) {
+            const int n = min((int)((uint32_t)(qtail - q0) / QSTRIDE), PB);
+            uint32_t e[PB];
+            pop_entries(qtail, n, true, e);
             qtail -= n * QSTRIDE;
-            heavy_lookup<NW, SEC, PB>(n, h, u, s, sec, lv, sfilt, e_re, e_im);
+            if constexpr (NW <= 2) {
+                if (sfilt) {
+#pragma unroll
+                    for (int b = 0; b < PB; ++b) {
+                        const bool pass = filter_pass<NW>(reinterpret_cast<const uint32_t*>(buf + (e[b] >> 16) * 4u), s, sfilt);
+                        if (b < n && pass) { q2 -= QSTRIDE; *reinterpret_cast<uint32_t*>(q2) = e[b]; }
+                    }
+                    // at most 3 survivors per lane stay behind, so the next filter round (<= PB more) always fits
+                    while (__any_sync(0xffffffffu, q2 <= q2end - 4 * QSTRIDE)) probe_round(buf);
+                    return;
+                }
+            }
+            resolve(buf, n, e, nullptr);
+        };
+        auto drain = [&](const unsigned char* __restrict__ buf) {  // before a tile buffer is released: its offsets die with it
+            while (__any_sync(0xffffffffu, qtail != q0)) pop_round(buf);
+            while (__any_sync(0xffffffffu, q2 != q2end)) probe_round(buf);
         };
         // branch-free: the entry is always written at the tail, the tail only advances for a live coupling
         auto push = [&](double h, uint32_t entry) {
@@ -608,9 +664,7 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
             have_resident = resident;
             const uint32_t tl_kind = sv.tiles[t].kind, tl_count = sv.tiles[t].count;
             process(smem + (size_t)b * buf_bytes, tl_kind, tl_count);
-            if constexpr (LK == kLookHash) {
-                while (__any_sync(0xffffffffu, qtail != q0)) pop_round(smem + (size_t)b * buf_bytes);
-            }
+            if constexpr (LK == kLookHash) drain(smem + (size_t)b * buf_bytes);
             if (!resident) __syncthreads();  // every thread is done with buffer b before it is refilled
         }
 

@@ -163,7 +163,7 @@ constexpr int kThreads = 256;
 constexpr int kSlicedThreads[6] = {1024, 512, 256, 1024, 512, 256};
 constexpr int kSlicedCtasPerSm[6] = {1, 2, 4, 1, 2, 4};
 constexpr bool kSlicedFilter[6] = {false, false, false, true, false, false};
-constexpr size_t kSlicedCap[6] = {112640, 55296, 26624, 47104, 36864, 18432};
+constexpr size_t kSlicedCap[6] = {112640, 55296, 26624, 36864, 36864, 18432};  // [3]: 2 x 36 KB tiles + 64 KB queue + 64 KB filter + 24 KB survivor queue
 constexpr size_t kSlicedMaxBlob = 16384;
 
 static int tile_cap_for(int nw32, int64_t K) {
@@ -471,10 +471,11 @@ static int launch_sliced_cfg(naqs_table_t* t, const uint64_t* d_states, const vo
     // the Bloom filter rides along only in the 1-CTA-per-SM shape (it needs 64 KB of shared memory)
     const bool use_filter = kSlicedFilter[TL] && t->filter_valid;
     const size_t filter_offset = queue_offset + queue_bytes;
-    const size_t smem = filter_offset + (use_filter ? kFilterBytes : 0);
+    const size_t q2_bytes = (size_t)kQueue2Cap * 4 * THREADS;  // survivors of the filter stage (sliced.cuh), behind the filter
+    const size_t smem = filter_offset + (use_filter ? kFilterBytes + q2_bytes : 0);
     auto kern = eloc_sliced_kernel<NW, NN, THREADS, kSlicedCtasPerSm[TL], LK, SEC, KEYORDER, PSI32>;
     NAQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(2 * cap + queue_bytes + (kSlicedFilter[TL] ? kFilterBytes : 0))));
+                                   (int)(2 * cap + queue_bytes + (kSlicedFilter[TL] ? kFilterBytes + (size_t)kQueue2Cap * 4 * THREADS : 0))));
     LookupView lv = t->lookup();
     if (!use_filter) lv.filter = nullptr;
     double2* partial = nullptr;
