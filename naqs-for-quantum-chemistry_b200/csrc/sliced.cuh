@@ -513,7 +513,7 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
             const uint32_t* u[PB];
 #pragma unroll
             for (int b = 0; b < PB; ++b) {
-                h[b] = *reinterpret_cast<const double*>(buf + (e[b] & 0xffffu) * 8u);
+                h[b] = *reinterpret_cast<const double*>(buf + (e[b] & 0xffffu));
                 u[b] = reinterpret_cast<const uint32_t*>(buf + (e[b] >> 16) * 4u);
             }
             heavy_lookup<NW, SEC, PB>(n, h, u, s, sec, lv, filt, e_re, e_im);
@@ -549,12 +549,17 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
             while (__any_sync(0xffffffffu, q2 != q2end)) probe_round(buf);
         };
         // branch-free: the entry is always written at the tail, the tail only advances for a live coupling
+        const uint32_t q_adv = valid ? QSTRIDE : 0u;  // an invalid lane never keeps an entry
         auto push = [&](double h, uint32_t entry) {
             *reinterpret_cast<uint32_t*>(qtail) = entry;
-            if (h != 0.0 && valid) qtail += QSTRIDE;
+            qtail += (h != 0.0) ? q_adv : 0u;
         };
 
         auto process = [&](const unsigned char* __restrict__ buf, const uint32_t tl_kind, const uint32_t tl_count) {
+            // queue entry of group 0 of the first record: LUT byte offset | (flip-mask offset / 4) << 16; one add per record
+            constexpr uint32_t EB_FIRST = (uint32_t)(64 * NN + UB) | ((uint32_t)(64 * NN / 4) << 16);
+            constexpr uint32_t EB_STEP_A = (uint32_t)REC_A | ((uint32_t)(REC_A / 4) << 16), EB_STEP_B = (uint32_t)REC_B | ((uint32_t)(REC_B / 4) << 16);
+            [[maybe_unused]] uint32_t ebase = EB_FIRST;
             if (tl_kind == kSecA) {
                 const unsigned char* rec = buf;
                 for (uint32_t r = 0; r < tl_count; ++r, rec += REC_A) {
@@ -578,13 +583,14 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                             else emit_batch<NW, SEC, KEYORDER, false, 4>(h, uu[j0 / 4], s, valid, sec, lv, e_re, e_im);
                         }
                     } else {
-                        // entry = (LUT entry offset / 8) | (flip-mask offset / 4) << 16, both relative to the tile buffer
-                        const uint32_t ebase = ((uint32_t)(L - buf) >> 3) | (((uint32_t)(reinterpret_cast<const unsigned char*>(U) - buf) >> 2) << 16);
+                        // entry = byte offset of the LUT entry | (flip-mask offset / 4) << 16, both relative to the tile buffer
+                        // (tiles of the hash shapes are < 64 KB); ebase follows the record pointer
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const uint32_t idx = (P >> (4 * j)) & 15u;
-                            push(*reinterpret_cast<const double*>(L + j * 128 + idx * 8), ebase + j * (16u + ((uint32_t)NW << 16)) + idx);
+                            const uint32_t off = j == 0 ? ((P << 3) & 0x78u) : ((P >> (4 * j - 3)) & 0x78u);
+                            push(*reinterpret_cast<const double*>(L + j * 128 + off), ebase + j * (128u + ((uint32_t)NW << 16)) + off);
                         }
+                        ebase += EB_STEP_A;
                         while (__any_sync(0xffffffffu, qtail > q0 + (kQueueCap - 8) * QSTRIDE)) pop_round(buf);
                     }
                 }
@@ -607,12 +613,12 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                         if constexpr (PSI32) emit_batch32<SEC, 5>(h, uu, a0, base_hi, valid, sec8, e_re, e_im);
                         else emit_batch<NW, SEC, KEYORDER, false, 5>(h, uu, s, valid, sec, lv, e_re, e_im);
                     } else {
-                        const uint32_t ebase = ((uint32_t)(L - buf) >> 3) | (((uint32_t)(reinterpret_cast<const unsigned char*>(U) - buf) >> 2) << 16);
 #pragma unroll
                         for (int j = 0; j < 5; ++j) {
-                            const uint32_t idx = (P >> (6 * j)) & 63u;
-                            push(*reinterpret_cast<const double*>(L + j * 512 + idx * 8), ebase + j * (64u + ((uint32_t)NW << 16)) + idx);
+                            const uint32_t off = j == 0 ? ((P << 3) & 0x1f8u) : ((P >> (6 * j - 3)) & 0x1f8u);
+                            push(*reinterpret_cast<const double*>(L + j * 512 + off), ebase + j * (512u + ((uint32_t)NW << 16)) + off);
                         }
+                        ebase += EB_STEP_B;
                         while (__any_sync(0xffffffffu, qtail > q0 + (kQueueCap - 8) * QSTRIDE)) pop_round(buf);
                     }
                 }

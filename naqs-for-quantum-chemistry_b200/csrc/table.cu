@@ -165,6 +165,7 @@ constexpr int kSlicedCtasPerSm[6] = {1, 2, 4, 1, 2, 4};
 constexpr bool kSlicedFilter[6] = {false, false, false, true, false, false};
 constexpr size_t kSlicedCap[6] = {112640, 55296, 26624, 36864, 36864, 18432};  // [3]: 2 x 36 KB tiles + 64 KB queue + 64 KB filter + 24 KB survivor queue
 constexpr size_t kSlicedMaxBlob = 16384;
+static_assert(kSlicedCap[3] < 65536 && kSlicedCap[4] < 65536 && kSlicedCap[5] < 65536, "queue entries of the hash shapes hold 16-bit byte offsets into a tile");
 
 static int tile_cap_for(int nw32, int64_t K) {
     // keep a tile <= ~56 KB so four CTAs of 256 threads fit one SM; whole table in one tile when it fits
