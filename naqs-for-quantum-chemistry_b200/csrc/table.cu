@@ -482,7 +482,7 @@ static int launch_sliced_cfg(naqs_table_t* t, const uint64_t* d_states, const vo
     double2* partial = nullptr;
     uint32_t* need_bits = nullptr;
     if (n_chunks > 1 || KEYORDER) {
-        const size_t bitmap_bytes = KEYORDER ? (((size_t)M / 8 + 255) & ~(size_t)255) : 0;
+        const size_t bitmap_bytes = KEYORDER ? ((((size_t)M + 31) / 32 * 4 + 255) & ~(size_t)255) : 0;  // whole 32-bit words, >= 256 B
         const size_t need = (size_t)n_chunks * M * sizeof(double2) + bitmap_bytes;
         if (t->partial_bytes < need) {
             cudaFree(t->d_partial); t->d_partial = nullptr; t->partial_bytes = 0;
