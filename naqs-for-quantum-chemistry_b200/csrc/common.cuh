@@ -122,8 +122,8 @@ __host__ __device__ inline unsigned long long mix64(unsigned long long x) {
     return x;
 }
 // Multiplicative (Fibonacci) hashing: the top bits of key * odd-constant depend on every key bit.  Two independent
-// products give the bucket index / first filter position and the second filter position — 2 IMAD + 3 SHF per key of
-// <= 32 bits.  Table capacities are powers of two <= 2^31.
+// products give the bucket index / filter word and the two bit positions inside that word — 2 IMAD + a few SHF per key
+// of <= 32 bits.  Table capacities are powers of two <= 2^31.
 __host__ __device__ inline uint32_t hash32(unsigned long long k0, unsigned long long k1) {
     return (uint32_t)k0 * 0x9E3779B1u + (uint32_t)(k0 >> 32) * 0x85EBCA6Bu + (uint32_t)k1 * 0xC2B2AE35u +
            (uint32_t)(k1 >> 32) * 0x27D4EB2Fu;
@@ -136,13 +136,17 @@ __host__ __device__ inline unsigned long long hash_slot(unsigned long long k0, u
 }
 
 // Bloom filter of the hash lookup: 2^19 bits = 64 KB, copied into shared memory by every CTA of the 1024-thread launch
-// shape.  In a sparse VMC batch almost every coupled state is NOT in the table; the filter answers those with two
-// shared-memory reads instead of a global sector read.  Built only while it has >= 4 bits per key.
+// shape.  In a sparse VMC batch almost every coupled state is NOT in the table; the filter answers those from shared
+// memory instead of a global sector read.  Blocked: both bits of a key live in ONE 32-bit word (one LDS per test) — the
+// word from the top bits of the bucket hash, the two bit positions from the top bits of a second product.  Built only
+// while it has >= 4 bits per key.
 constexpr uint32_t kFilterBits = 1u << 19;
 constexpr uint32_t kFilterBytes = kFilterBits / 8;
-__host__ __device__ inline void filter_positions(unsigned long long k0, uint32_t h, uint32_t& b1, uint32_t& b2) {
-    b1 = h >> (32 - 19);
-    b2 = hash32b(k0) >> (32 - 19);
+__host__ __device__ inline void filter_word_bits(unsigned long long k0, uint32_t h, uint32_t& word, uint32_t& b1, uint32_t& b2) {
+    const uint32_t hb = hash32b(k0);
+    word = h >> (32 - 14);
+    b1 = hb >> 27;
+    b2 = (hb >> 22) & 31u;
 }
 
 }  // namespace naqs

@@ -318,20 +318,18 @@ __device__ __forceinline__ void emit_batch(const double (&h)[B], const uint32_t 
     }
 }
 
-// Stage 1 of the two-stage hash lookup (launch shape with the shared-memory Bloom filter): is the coupled state s ^ u
-// possibly in the table?  A clear filter bit proves it is not — ~90 % of the couplings of a large-sector batch end here
-// without touching global memory.
+// Bloom-filter test of a coupled state (launch shape with the filter in shared memory): a clear bit proves the key is not
+// in the table — ~90 % of the couplings of a large-sector batch end here without touching global memory.  Cheap enough
+// (one LDS, two IMAD, a few shifts) to run for EVERY (state, group) pair in the light path, before anything is queued.
 template <int NW>
-__device__ __forceinline__ bool filter_pass(const uint32_t* __restrict__ u, const uint32_t (&s)[NW], const uint32_t* __restrict__ sfilt) {
+__device__ __forceinline__ bool filter_pass(const uint32_t (&j)[NW], const uint32_t* __restrict__ sfilt) {
     static_assert(NW <= 2, "the Bloom filter accompanies the bucketed table (keys <= 63 bits)");
-    uint32_t j[NW];
-#pragma unroll
-    for (int w = 0; w < NW; ++w) j[w] = s[w] ^ u[w];
     unsigned long long k0, k1;
     key_words64<NW>(j, k0, k1);
-    uint32_t b1, b2;
-    filter_positions(k0, hash32(k0, 0ull), b1, b2);
-    return ((sfilt[b1 >> 5] >> (b1 & 31)) & (sfilt[b2 >> 5] >> (b2 & 31)) & 1u) != 0;
+    uint32_t w, b1, b2;
+    filter_word_bits(k0, hash32(k0, 0ull), w, b1, b2);
+    const uint32_t word = sfilt[w];
+    return ((word >> b1) & (word >> b2) & 1u) != 0;
 }
 
 // Hash-lookup ("heavy") epilogue of up to B couplings of one thread: sector filter (hamiltonian.py:328), shared-memory
@@ -357,11 +355,7 @@ __device__ __forceinline__ void heavy_lookup(int n, const double (&h)[B], const 
         if constexpr (NW <= 2) {
             const uint32_t hh = hash32(k0[b], 0ull);
             slot[b] = hh >> lv.bshift;
-            if (sfilt) {  // a clear bit proves the key is not in the table: no global access at all
-                uint32_t b1, b2;
-                filter_positions(k0[b], hh, b1, b2);
-                on[b] = on[b] & (((sfilt[b1 >> 5] >> (b1 & 31)) & (sfilt[b2 >> 5] >> (b2 & 31)) & 1u) != 0);
-            }
+            if (sfilt) on[b] = on[b] & filter_pass<NW>(j, sfilt);  // a clear bit proves the key is not in the table
         } else {
             slot[b] = (unsigned)hash_slot(k0[b], k1[b], lv.shift);
         }
@@ -412,7 +406,6 @@ __device__ __forceinline__ void heavy_lookup(int n, const double (&h)[B], const 
 }
 
 constexpr int kQueueCap = 16;  // pending couplings per thread (hash mode)
-constexpr int kQueue2Cap = 6;  // couplings per thread that passed the Bloom filter and await their table probe (filter shape only)
 
 // One state per thread.  Each CTA owns state blocks blockIdx.x, blockIdx.x + gridDim.x, ... and walks the
 // tiles [tile_lo, tile_hi) of its chunk (blockIdx.y) for each of them; with a single tile the table stays
@@ -486,73 +479,47 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
         const uint32_t a0 = base_lo ^ (s[0] << 3);  // PSI32 only
         double e_re = 0.0, e_im = 0.0;
 
-        // hash mode: couplings with H != 0 are parked in a per-thread queue (shared memory, [slot][thread] layout, one
-        // 32-bit word each: LUT entry offset | flip-mask offset inside the current tile) and resolved in warp-wide
-        // rounds, so the expensive part (sector test, hashing, probing) runs with most lanes busy although only a
-        // fraction of the (state, group) pairs couples.  The queue is drained before a tile buffer is released.
+        // hash mode: a coupling survives the light path when H != 0 AND (filter shape) its coupled state passes the Bloom
+        // filter in shared memory — a few % of the (state, group) pairs of a large-sector batch.  Survivors are parked in a
+        // per-thread queue (shared memory, [slot][thread] layout, one 32-bit word each: LUT byte offset | flip-mask offset
+        // inside the current tile) and resolved in warp-wide rounds, so the expensive part (bucket probe in global memory,
+        // key compare) runs with many lanes busy.  The queue is drained before a tile buffer is released.
         constexpr uint32_t QSTRIDE = THREADS * 4;  // bytes between consecutive queue slots of one thread
         unsigned char* const q0 = smem + queue_offset + threadIdx.x * 4;
         unsigned char* qtail = q0;            // the queue holds (qtail - q0) / QSTRIDE couplings
         constexpr int PB = 2;  // couplings resolved per thread and round
-        // Two stages when the Bloom filter is present.  Stage 1 (filter_round) pops couplings, tests the filter in shared
-        // memory and moves the ~10 % survivors to a second per-thread queue; stage 2 (probe_round) runs once some lane
-        // holds >= 4 survivors and does the global bucket probes with many lanes busy — a round that waits on L2 for two
-        // lanes out of 32 was the largest stall of the one-stage version.  Without a filter a single stage does it all.
-        unsigned char* const q2end = smem + filter_offset + kFilterBytes + (size_t)kQueue2Cap * QSTRIDE + threadIdx.x * 4;
-        unsigned char* q2 = q2end;            // survivors occupy [q2, q2end), growing downwards
-        auto pop_entries = [&](unsigned char* base, int n, bool down, uint32_t (&e)[PB]) {
-#pragma unroll
-            for (int b = 0; b < PB; ++b) {
-                // always read a valid slot (an arbitrary one of the queue when it is shorter than b + 1): no branch, lanes are masked by n
-                const unsigned char* slot = down ? (b < n ? base - (b + 1) * QSTRIDE : q0) : (b < n ? base + b * QSTRIDE : q0);
-                e[b] = *reinterpret_cast<const uint32_t*>(slot);
-            }
-        };
-        auto resolve = [&](const unsigned char* __restrict__ buf, int n, const uint32_t (&e)[PB], const uint32_t* filt) {
+        auto pop_round = [&](const unsigned char* __restrict__ buf) {
+            const int n = min((int)((uint32_t)(qtail - q0) / QSTRIDE), PB);
             double h[PB];
             const uint32_t* u[PB];
 #pragma unroll
             for (int b = 0; b < PB; ++b) {
-                h[b] = *reinterpret_cast<const double*>(buf + (e[b] & 0xffffu));
-                u[b] = reinterpret_cast<const uint32_t*>(buf + (e[b] >> 16) * 4u);
+                // always read a valid slot (the oldest one when the queue is shorter than b + 1): no branch, lanes are masked by n
+                const unsigned char* slot = b < n ? qtail - (b + 1) * QSTRIDE : q0;
+                const uint32_t e = *reinterpret_cast<const uint32_t*>(slot);
+                h[b] = *reinterpret_cast<const double*>(buf + (e & 0xffffu));
+                u[b] = reinterpret_cast<const uint32_t*>(buf + (e >> 16) * 4u);
             }
-            heavy_lookup<NW, SEC, PB>(n, h, u, s, sec, lv, filt, e_re, e_im);
-        };
-        auto probe_round = [&](const unsigned char* __restrict__ buf) {
-            const int n = min((int)((uint32_t)(q2end - q2) / QSTRIDE), PB);
-            uint32_t e[PB];
-            pop_entries(q2, n, false, e);
-            q2 += n * QSTRIDE;
-            resolve(buf, n, e, nullptr);
-        };
-        auto pop_round = [&](const unsigned char* __restrict__ buf) {
-            const int n = min((int)((uint32_t)(qtail - q0) / QSTRIDE), PB);
-            uint32_t e[PB];
-            pop_entries(qtail, n, true, e);
             qtail -= n * QSTRIDE;
-            if constexpr (NW <= 2) {
-                if (sfilt) {
-#pragma unroll
-                    for (int b = 0; b < PB; ++b) {
-                        const bool pass = filter_pass<NW>(reinterpret_cast<const uint32_t*>(buf + (e[b] >> 16) * 4u), s, sfilt);
-                        if (b < n && pass) { q2 -= QSTRIDE; *reinterpret_cast<uint32_t*>(q2) = e[b]; }
-                    }
-                    // at most 3 survivors per lane stay behind, so the next filter round (<= PB more) always fits
-                    while (__any_sync(0xffffffffu, q2 <= q2end - 4 * QSTRIDE)) probe_round(buf);
-                    return;
-                }
-            }
-            resolve(buf, n, e, nullptr);
+            heavy_lookup<NW, SEC, PB>(n, h, u, s, sec, lv, nullptr, e_re, e_im);  // the filter was consulted before queueing
         };
         auto drain = [&](const unsigned char* __restrict__ buf) {  // before a tile buffer is released: its offsets die with it
             while (__any_sync(0xffffffffu, qtail != q0)) pop_round(buf);
-            while (__any_sync(0xffffffffu, q2 != q2end)) probe_round(buf);
         };
         // branch-free: the entry is always written at the tail, the tail only advances for a live coupling
         const uint32_t q_adv = valid ? QSTRIDE : 0u;  // an invalid lane never keeps an entry
-        auto push = [&](double h, uint32_t entry) {
+        auto push = [&](double h, const uint32_t* __restrict__ u, uint32_t entry) {
             *reinterpret_cast<uint32_t*>(qtail) = entry;
-            qtail += (h != 0.0) ? q_adv : 0u;
+            bool live = h != 0.0;
+            if constexpr (NW <= 2) {
+                if (sfilt) {  // warp-uniform
+                    uint32_t j[NW];
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) j[w] = s[w] ^ u[w];
+                    live = live & filter_pass<NW>(j, sfilt);
+                }
+            }
+            qtail += live ? q_adv : 0u;
         };
 
         auto process = [&](const unsigned char* __restrict__ buf, const uint32_t tl_kind, const uint32_t tl_count) {
@@ -588,7 +555,7 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const uint32_t off = j == 0 ? ((P << 3) & 0x78u) : ((P >> (4 * j - 3)) & 0x78u);
-                            push(*reinterpret_cast<const double*>(L + j * 128 + off), ebase + j * (128u + ((uint32_t)NW << 16)) + off);
+                            push(*reinterpret_cast<const double*>(L + j * 128 + off), U + j * NW, ebase + j * (128u + ((uint32_t)NW << 16)) + off);
                         }
                         ebase += EB_STEP_A;
                         while (__any_sync(0xffffffffu, qtail > q0 + (kQueueCap - 8) * QSTRIDE)) pop_round(buf);
@@ -616,7 +583,7 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
 #pragma unroll
                         for (int j = 0; j < 5; ++j) {
                             const uint32_t off = j == 0 ? ((P << 3) & 0x1f8u) : ((P >> (6 * j - 3)) & 0x1f8u);
-                            push(*reinterpret_cast<const double*>(L + j * 512 + off), ebase + j * (512u + ((uint32_t)NW << 16)) + off);
+                            push(*reinterpret_cast<const double*>(L + j * 512 + off), U + j * NW, ebase + j * (512u + ((uint32_t)NW << 16)) + off);
                         }
                         ebase += EB_STEP_B;
                         while (__any_sync(0xffffffffu, qtail > q0 + (kQueueCap - 8) * QSTRIDE)) pop_round(buf);

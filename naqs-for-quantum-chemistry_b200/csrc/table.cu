@@ -119,10 +119,9 @@ __global__ void bucket_insert_kernel(HashBucket* buckets, unsigned bmask, int bs
 __global__ void filter_build_kernel(uint32_t* filter, const uint64_t* __restrict__ keys, int words, int64_t n, Sector sec) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !key_in_sector(keys + i * words, words, sec)) return;
-    uint32_t b1, b2;
-    filter_positions(keys[i * words], hash32(keys[i * words], 0ull), b1, b2);
-    atomicOr(&filter[b1 >> 5], 1u << (b1 & 31));
-    atomicOr(&filter[b2 >> 5], 1u << (b2 & 31));
+    uint32_t w, b1, b2;
+    filter_word_bits(keys[i * words], hash32(keys[i * words], 0ull), w, b1, b2);
+    atomicOr(&filter[w], (1u << b1) | (1u << b2));
 }
 
 __global__ void widen_keys_kernel(const void* __restrict__ in, int itemsize, int64_t n, uint64_t* __restrict__ out) {
@@ -163,7 +162,7 @@ constexpr int kThreads = 256;
 constexpr int kSlicedThreads[6] = {1024, 512, 256, 1024, 512, 256};
 constexpr int kSlicedCtasPerSm[6] = {1, 2, 4, 1, 2, 4};
 constexpr bool kSlicedFilter[6] = {false, false, false, true, false, false};
-constexpr size_t kSlicedCap[6] = {112640, 55296, 26624, 36864, 36864, 18432};  // [3]: 2 x 36 KB tiles + 64 KB queue + 64 KB filter + 24 KB survivor queue
+constexpr size_t kSlicedCap[6] = {112640, 55296, 26624, 47104, 36864, 18432};  // [3]: 2 x 46 KB tiles + 64 KB queue + 64 KB filter
 constexpr size_t kSlicedMaxBlob = 16384;
 static_assert(kSlicedCap[3] < 65536 && kSlicedCap[4] < 65536 && kSlicedCap[5] < 65536, "queue entries of the hash shapes hold 16-bit byte offsets into a tile");
 
@@ -472,11 +471,10 @@ static int launch_sliced_cfg(naqs_table_t* t, const uint64_t* d_states, const vo
     // the Bloom filter rides along only in the 1-CTA-per-SM shape (it needs 64 KB of shared memory)
     const bool use_filter = kSlicedFilter[TL] && t->filter_valid;
     const size_t filter_offset = queue_offset + queue_bytes;
-    const size_t q2_bytes = (size_t)kQueue2Cap * 4 * THREADS;  // survivors of the filter stage (sliced.cuh), behind the filter
-    const size_t smem = filter_offset + (use_filter ? kFilterBytes + q2_bytes : 0);
+    const size_t smem = filter_offset + (use_filter ? kFilterBytes : 0);
     auto kern = eloc_sliced_kernel<NW, NN, THREADS, kSlicedCtasPerSm[TL], LK, SEC, KEYORDER, PSI32>;
     NAQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(2 * cap + queue_bytes + (kSlicedFilter[TL] ? kFilterBytes + (size_t)kQueue2Cap * 4 * THREADS : 0))));
+                                   (int)(2 * cap + queue_bytes + (kSlicedFilter[TL] ? kFilterBytes : 0))));
     LookupView lv = t->lookup();
     if (!use_filter) lv.filter = nullptr;
     double2* partial = nullptr;
