@@ -508,18 +508,30 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
         };
         // branch-free: the entry is always written at the tail, the tail only advances for a live coupling
         const uint32_t q_adv = valid ? QSTRIDE : 0u;  // an invalid lane never keeps an entry
-        auto push = [&](double h, const uint32_t* __restrict__ u, uint32_t entry) {
+        auto push = [&](double h, uint32_t entry) {
             *reinterpret_cast<uint32_t*>(qtail) = entry;
-            bool live = h != 0.0;
+            qtail += (h != 0.0) ? q_adv : 0u;
+        };
+        // the same with the Bloom filter consulted first (u: the group's flip mask, already in registers)
+        auto push_filtered = [&](double h, const uint32_t (&u)[NW], uint32_t entry) {
+            *reinterpret_cast<uint32_t*>(qtail) = entry;
             if constexpr (NW <= 2) {
-                if (sfilt) {  // warp-uniform
-                    uint32_t j[NW];
+                uint32_t j[NW];
 #pragma unroll
-                    for (int w = 0; w < NW; ++w) j[w] = s[w] ^ u[w];
-                    live = live & filter_pass<NW>(j, sfilt);
+                for (int w = 0; w < NW; ++w) j[w] = s[w] ^ u[w];
+                const bool pass = filter_pass<NW>(j, sfilt);
+                qtail += (pass && h != 0.0) ? q_adv : 0u;
+            }
+        };
+        // flip masks of G groups of a record as vector loads (NW <= 2 only: the filter exists for keys <= 63 bits)
+        auto load_masks = [&](const uint32_t* __restrict__ U, uint32_t (&uv)[8 * (NW <= 2 ? NW : 1)]) {
+            if constexpr (NW <= 2) {
+#pragma unroll
+                for (int q = 0; q < 2 * NW; ++q) {
+                    const uint4 v = reinterpret_cast<const uint4*>(U)[q];
+                    uv[4 * q] = v.x; uv[4 * q + 1] = v.y; uv[4 * q + 2] = v.z; uv[4 * q + 3] = v.w;
                 }
             }
-            qtail += live ? q_adv : 0u;
         };
 
         auto process = [&](const unsigned char* __restrict__ buf, const uint32_t tl_kind, const uint32_t tl_count) {
@@ -552,10 +564,23 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                     } else {
                         // entry = byte offset of the LUT entry | (flip-mask offset / 4) << 16, both relative to the tile buffer
                         // (tiles of the hash shapes are < 64 KB); ebase follows the record pointer
+                        if (NW <= 2 && sfilt) {  // warp-uniform
+                            uint32_t uv[8 * (NW <= 2 ? NW : 1)];
+                            load_masks(U, uv);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const uint32_t off = j == 0 ? ((P << 3) & 0x78u) : ((P >> (4 * j - 3)) & 0x78u);
-                            push(*reinterpret_cast<const double*>(L + j * 128 + off), U + j * NW, ebase + j * (128u + ((uint32_t)NW << 16)) + off);
+                            for (int j = 0; j < 8; ++j) {
+                                const uint32_t off = j == 0 ? ((P << 3) & 0x78u) : ((P >> (4 * j - 3)) & 0x78u);
+                                uint32_t uj[NW];
+#pragma unroll
+                                for (int w = 0; w < NW; ++w) uj[w] = uv[(j * NW + w) % (8 * (NW <= 2 ? NW : 1))];
+                                push_filtered(*reinterpret_cast<const double*>(L + j * 128 + off), uj, ebase + j * (128u + ((uint32_t)NW << 16)) + off);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const uint32_t off = j == 0 ? ((P << 3) & 0x78u) : ((P >> (4 * j - 3)) & 0x78u);
+                                push(*reinterpret_cast<const double*>(L + j * 128 + off), ebase + j * (128u + ((uint32_t)NW << 16)) + off);
+                            }
                         }
                         ebase += EB_STEP_A;
                         while (__any_sync(0xffffffffu, qtail > q0 + (kQueueCap - 8) * QSTRIDE)) pop_round(buf);
@@ -580,10 +605,23 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                         if constexpr (PSI32) emit_batch32<SEC, 5>(h, uu, a0, base_hi, valid, sec8, e_re, e_im);
                         else emit_batch<NW, SEC, KEYORDER, false, 5>(h, uu, s, valid, sec, lv, e_re, e_im);
                     } else {
+                        if (NW <= 2 && sfilt) {  // warp-uniform
+                            uint32_t uv[8 * (NW <= 2 ? NW : 1)];
+                            load_masks(U, uv);
 #pragma unroll
-                        for (int j = 0; j < 5; ++j) {
-                            const uint32_t off = j == 0 ? ((P << 3) & 0x1f8u) : ((P >> (6 * j - 3)) & 0x1f8u);
-                            push(*reinterpret_cast<const double*>(L + j * 512 + off), U + j * NW, ebase + j * (512u + ((uint32_t)NW << 16)) + off);
+                            for (int j = 0; j < 5; ++j) {
+                                const uint32_t off = j == 0 ? ((P << 3) & 0x1f8u) : ((P >> (6 * j - 3)) & 0x1f8u);
+                                uint32_t uj[NW];
+#pragma unroll
+                                for (int w = 0; w < NW; ++w) uj[w] = uv[(j * NW + w) % (8 * (NW <= 2 ? NW : 1))];
+                                push_filtered(*reinterpret_cast<const double*>(L + j * 512 + off), uj, ebase + j * (512u + ((uint32_t)NW << 16)) + off);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 5; ++j) {
+                                const uint32_t off = j == 0 ? ((P << 3) & 0x1f8u) : ((P >> (6 * j - 3)) & 0x1f8u);
+                                push(*reinterpret_cast<const double*>(L + j * 512 + off), ebase + j * (512u + ((uint32_t)NW << 16)) + off);
+                            }
                         }
                         ebase += EB_STEP_B;
                         while (__any_sync(0xffffffffu, qtail > q0 + (kQueueCap - 8) * QSTRIDE)) pop_round(buf);
