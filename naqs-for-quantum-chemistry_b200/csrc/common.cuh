@@ -111,8 +111,10 @@ struct LookupView {
     const HashBucket* buckets;  // [n_buckets] (kind HASH, keys <= 63 bits)
     unsigned bmask;          // n_buckets - 1
     int bshift;              // 32 - log2(n_buckets)
-    const uint32_t* filter;  // Bloom filter over the table keys (kFilterBits bits, 2 probes) or nullptr
+    const uint32_t* filter;  // blocked Bloom filter over the table keys (2^(32 - filter_wshift) words) or nullptr
     const float2* dense32;   // [2^N] complex64 copy of the dense table (unique keys + complex64 psi only) or nullptr
+    int filter_wshift;       // filter word = hash32 >> filter_wshift
+    int filter_in_smem;      // the launch copies the filter into shared memory (it has 2^14 words and the shape has room)
 };
 
 
@@ -135,16 +137,18 @@ __host__ __device__ inline unsigned long long hash_slot(unsigned long long k0, u
     return (unsigned long long)(hash32(k0, k1) >> shift);
 }
 
-// Bloom filter of the hash lookup: 2^19 bits = 64 KB, copied into shared memory by every CTA of the 1024-thread launch
-// shape.  In a sparse VMC batch almost every coupled state is NOT in the table; the filter answers those from shared
-// memory instead of a global sector read.  Blocked: both bits of a key live in ONE 32-bit word (one LDS per test) — the
-// word from the top bits of the bucket hash, the two bit positions from the top bits of a second product.  Built only
-// while it has >= 4 bits per key.
-constexpr uint32_t kFilterBits = 1u << 19;
-constexpr uint32_t kFilterBytes = kFilterBits / 8;
-__host__ __device__ inline void filter_word_bits(unsigned long long k0, uint32_t h, uint32_t& word, uint32_t& b1, uint32_t& b2) {
-    const uint32_t hb = hash32b(k0);
-    word = h >> (32 - 14);
+// Bloom filter of the hash lookups.  In a sparse VMC batch almost every coupled state is NOT in the table; the filter
+// answers those without the global sector read of a bucket / slot.  Blocked: both bits of a key live in ONE 32-bit word
+// (one load per test) — the word from the top bits of the table hash, the two bit positions from the top bits of a
+// second product.  2^14 words (64 KB, >= 4 bits per key) up to 2^17 keys — that size is copied into shared memory by
+// every CTA of the 1024-thread launch shape and consulted for every (state, group) pair; larger batches get >= 16 bits
+// per key, up to 2^22 words (16 MB, L2-resident), consulted from global memory before a bucket / slot probe.
+constexpr int kFilterLog2WordsSmem = 14, kFilterLog2WordsMax = 22;
+constexpr uint32_t kFilterBytes = (1u << kFilterLog2WordsSmem) * 4;  // the shared-memory copy
+__host__ __device__ inline void filter_word_bits(unsigned long long k0, unsigned long long k1, uint32_t h, int wshift,
+                                                 uint32_t& word, uint32_t& b1, uint32_t& b2) {
+    const uint32_t hb = hash32b(k0) + (uint32_t)k1 * 0x165667B1u + (uint32_t)(k1 >> 32) * 0xD3A2646Cu;
+    word = h >> wshift;
     b1 = hb >> 27;
     b2 = (hb >> 22) & 31u;
 }
@@ -188,8 +192,9 @@ struct naqs_table {
     int64_t hash_cap = 0, hash_alloc = 0;
     naqs::HashBucket* d_buckets = nullptr; // <= 63-bit keys: 128 B buckets of 4
     int64_t n_buckets = 0, bucket_alloc = 0;
-    uint32_t* d_filter = nullptr;          // Bloom filter storage (kFilterBytes)
+    uint32_t* d_filter = nullptr;          // Bloom filter storage (2^filter_log2w words, allocated for filter_alloc_log2w)
     bool filter_valid = false;
+    int filter_log2w = naqs::kFilterLog2WordsSmem, filter_alloc_log2w = -1;
     // generic workspace (scan / sort temporaries, host-path staging)
     void* d_ws = nullptr;
     size_t ws_bytes = 0;
@@ -208,7 +213,8 @@ struct naqs_table {
         return naqs::LookupView{d_dense, d_slots, (unsigned long long)(hash_cap - 1), lookup_kind, shift,
                                 d_buckets, (unsigned)(n_buckets > 0 ? n_buckets - 1 : 0), bshift,
                                 filter_valid ? d_filter : nullptr,
-                                dense32_valid ? (d_dense32_ext ? d_dense32_ext : d_dense32) : nullptr};
+                                dense32_valid ? (d_dense32_ext ? d_dense32_ext : d_dense32) : nullptr,
+                                32 - filter_log2w, 0};
     }
 };
 

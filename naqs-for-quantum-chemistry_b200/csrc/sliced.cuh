@@ -321,14 +321,15 @@ __device__ __forceinline__ void emit_batch(const double (&h)[B], const uint32_t 
 // Bloom-filter test of a coupled state (launch shape with the filter in shared memory): a clear bit proves the key is not
 // in the table — ~90 % of the couplings of a large-sector batch end here without touching global memory.  Cheap enough
 // (one LDS, two IMAD, a few shifts) to run for EVERY (state, group) pair in the light path, before anything is queued.
+// The same test against the filter in GLOBAL memory (larger batches, or shapes without room for the copy) runs in the
+// probe rounds, where it replaces most bucket reads (HBM sectors of a table far larger than L2) by L2 hits.
 template <int NW>
-__device__ __forceinline__ bool filter_pass(const uint32_t (&j)[NW], const uint32_t* __restrict__ sfilt) {
-    static_assert(NW <= 2, "the Bloom filter accompanies the bucketed table (keys <= 63 bits)");
+__device__ __forceinline__ bool filter_pass(const uint32_t (&j)[NW], const uint32_t* __restrict__ filt, int wshift) {
     unsigned long long k0, k1;
     key_words64<NW>(j, k0, k1);
     uint32_t w, b1, b2;
-    filter_word_bits(k0, hash32(k0, 0ull), w, b1, b2);
-    const uint32_t word = sfilt[w];
+    filter_word_bits(k0, k1, hash32(k0, k1), wshift, w, b1, b2);
+    const uint32_t word = filt[w];
     return ((word >> b1) & (word >> b2) & 1u) != 0;
 }
 
@@ -339,7 +340,7 @@ __device__ __forceinline__ bool filter_pass(const uint32_t (&j)[NW], const uint3
 // of all B couplings are issued before any is examined, so their L2 latencies overlap.
 template <int NW, bool SEC, int B>
 __device__ __forceinline__ void heavy_lookup(int n, const double (&h)[B], const uint32_t* const (&u)[B], const uint32_t (&s)[NW],
-                                             const Sector& sec, const LookupView& lv, const uint32_t* __restrict__ sfilt,
+                                             const Sector& sec, const LookupView& lv, const uint32_t* __restrict__ filt,
                                              double& e_re, double& e_im) {
     unsigned long long k0[B], k1[B];
     unsigned slot[B];
@@ -352,13 +353,9 @@ __device__ __forceinline__ void heavy_lookup(int n, const double (&h)[B], const 
         for (int w = 0; w < NW; ++w) j[w] = on[b] ? (s[w] ^ u[b][w]) : s[w];
         if constexpr (SEC) on[b] = on[b] & in_sector<NW>(j, sec);
         key_words64<NW>(j, k0[b], k1[b]);
-        if constexpr (NW <= 2) {
-            const uint32_t hh = hash32(k0[b], 0ull);
-            slot[b] = hh >> lv.bshift;
-            if (sfilt) on[b] = on[b] & filter_pass<NW>(j, sfilt);  // a clear bit proves the key is not in the table
-        } else {
-            slot[b] = (unsigned)hash_slot(k0[b], k1[b], lv.shift);
-        }
+        if (filt) on[b] = on[b] & filter_pass<NW>(j, filt, lv.filter_wshift);  // a clear bit proves the key is not in the table
+        if constexpr (NW <= 2) slot[b] = hash32(k0[b], 0ull) >> lv.bshift;
+        else slot[b] = (unsigned)hash_slot(k0[b], k1[b], lv.shift);
     }
     if constexpr (NW <= 2) {
         // bucketed table: the 4 keys of a bucket are one sector; all B first probes are in flight together
@@ -433,13 +430,16 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
         mbar_init(&mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    const uint32_t* sfilt = nullptr;  // Bloom filter of the table keys in shared memory (hash lookup, 1024-thread shape)
+    const uint32_t* sfilt = nullptr;  // Bloom filter of the table keys in shared memory (hash lookup, 1024-thread shape, <= 2^17 keys)
+    const uint32_t* gfilt = nullptr;  // ... or in global memory (L2), consulted in the probe rounds
     if constexpr (LK == kLookHash) {
-        if (lv.filter) {
+        if (lv.filter && lv.filter_in_smem) {
             uint4* dst = reinterpret_cast<uint4*>(smem + filter_offset);
             const uint4* src = reinterpret_cast<const uint4*>(lv.filter);
             for (uint32_t i = threadIdx.x; i < kFilterBytes / 16; i += THREADS) dst[i] = __ldg(src + i);
             sfilt = reinterpret_cast<const uint32_t*>(smem + filter_offset);
+        } else {
+            gfilt = lv.filter;
         }
     }
     __syncthreads();
@@ -501,7 +501,7 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                 u[b] = reinterpret_cast<const uint32_t*>(buf + (e >> 16) * 4u);
             }
             qtail -= n * QSTRIDE;
-            heavy_lookup<NW, SEC, PB>(n, h, u, s, sec, lv, nullptr, e_re, e_im);  // the filter was consulted before queueing
+            heavy_lookup<NW, SEC, PB>(n, h, u, s, sec, lv, gfilt, e_re, e_im);  // a shared-memory filter was consulted before queueing
         };
         auto drain = [&](const unsigned char* __restrict__ buf) {  // before a tile buffer is released: its offsets die with it
             while (__any_sync(0xffffffffu, qtail != q0)) pop_round(buf);
@@ -512,26 +512,22 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
             *reinterpret_cast<uint32_t*>(qtail) = entry;
             qtail += (h != 0.0) ? q_adv : 0u;
         };
-        // the same with the Bloom filter consulted first (u: the group's flip mask, already in registers)
-        auto push_filtered = [&](double h, const uint32_t (&u)[NW], uint32_t entry) {
+        // the same with the shared-memory Bloom filter consulted first; U = the record's flip masks, group j
+        auto push_filtered = [&](double h, const uint32_t* __restrict__ U, int j, const uint4& ua, const uint4& ub, uint32_t entry) {
             *reinterpret_cast<uint32_t*>(qtail) = entry;
-            if constexpr (NW <= 2) {
-                uint32_t j[NW];
-#pragma unroll
-                for (int w = 0; w < NW; ++w) j[w] = s[w] ^ u[w];
-                const bool pass = filter_pass<NW>(j, sfilt);
-                qtail += (pass && h != 0.0) ? q_adv : 0u;
+            uint32_t k[NW];
+            if constexpr (NW == 1) {        // masks of the 8 groups preloaded as two vectors
+                const uint32_t uv[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
+                k[0] = s[0] ^ uv[j];
+            } else if constexpr (NW == 2) {
+                const uint2 v = reinterpret_cast<const uint2*>(U)[j];
+                k[0] = s[0] ^ v.x; k[1] = s[1] ^ v.y;
+            } else {
+                const uint4 v = reinterpret_cast<const uint4*>(U)[j];
+                k[0] = s[0] ^ v.x; k[1] = s[1] ^ v.y; k[2] = s[2] ^ v.z; k[3] = s[3] ^ v.w;
             }
-        };
-        // flip masks of G groups of a record as vector loads (NW <= 2 only: the filter exists for keys <= 63 bits)
-        auto load_masks = [&](const uint32_t* __restrict__ U, uint32_t (&uv)[8 * (NW <= 2 ? NW : 1)]) {
-            if constexpr (NW <= 2) {
-#pragma unroll
-                for (int q = 0; q < 2 * NW; ++q) {
-                    const uint4 v = reinterpret_cast<const uint4*>(U)[q];
-                    uv[4 * q] = v.x; uv[4 * q + 1] = v.y; uv[4 * q + 2] = v.z; uv[4 * q + 3] = v.w;
-                }
-            }
+            const bool pass = filter_pass<NW>(k, sfilt, lv.filter_wshift);
+            qtail += (pass && h != 0.0) ? q_adv : 0u;
         };
 
         auto process = [&](const unsigned char* __restrict__ buf, const uint32_t tl_kind, const uint32_t tl_count) {
@@ -564,16 +560,13 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                     } else {
                         // entry = byte offset of the LUT entry | (flip-mask offset / 4) << 16, both relative to the tile buffer
                         // (tiles of the hash shapes are < 64 KB); ebase follows the record pointer
-                        if (NW <= 2 && sfilt) {  // warp-uniform
-                            uint32_t uv[8 * (NW <= 2 ? NW : 1)];
-                            load_masks(U, uv);
+                        if (sfilt) {  // warp-uniform
+                            uint4 ua = make_uint4(0, 0, 0, 0), ub = ua;
+                            if constexpr (NW == 1) { ua = *reinterpret_cast<const uint4*>(U); ub = *reinterpret_cast<const uint4*>(U + 4); }
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const uint32_t off = j == 0 ? ((P << 3) & 0x78u) : ((P >> (4 * j - 3)) & 0x78u);
-                                uint32_t uj[NW];
-#pragma unroll
-                                for (int w = 0; w < NW; ++w) uj[w] = uv[(j * NW + w) % (8 * (NW <= 2 ? NW : 1))];
-                                push_filtered(*reinterpret_cast<const double*>(L + j * 128 + off), uj, ebase + j * (128u + ((uint32_t)NW << 16)) + off);
+                                push_filtered(*reinterpret_cast<const double*>(L + j * 128 + off), U, j, ua, ub, ebase + j * (128u + ((uint32_t)NW << 16)) + off);
                             }
                         } else {
 #pragma unroll
@@ -605,16 +598,13 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                         if constexpr (PSI32) emit_batch32<SEC, 5>(h, uu, a0, base_hi, valid, sec8, e_re, e_im);
                         else emit_batch<NW, SEC, KEYORDER, false, 5>(h, uu, s, valid, sec, lv, e_re, e_im);
                     } else {
-                        if (NW <= 2 && sfilt) {  // warp-uniform
-                            uint32_t uv[8 * (NW <= 2 ? NW : 1)];
-                            load_masks(U, uv);
+                        if (sfilt) {  // warp-uniform
+                            uint4 ua = make_uint4(0, 0, 0, 0), ub = ua;
+                            if constexpr (NW == 1) { ua = *reinterpret_cast<const uint4*>(U); ub = *reinterpret_cast<const uint4*>(U + 4); }
 #pragma unroll
                             for (int j = 0; j < 5; ++j) {
                                 const uint32_t off = j == 0 ? ((P << 3) & 0x1f8u) : ((P >> (6 * j - 3)) & 0x1f8u);
-                                uint32_t uj[NW];
-#pragma unroll
-                                for (int w = 0; w < NW; ++w) uj[w] = uv[(j * NW + w) % (8 * (NW <= 2 ? NW : 1))];
-                                push_filtered(*reinterpret_cast<const double*>(L + j * 512 + off), uj, ebase + j * (512u + ((uint32_t)NW << 16)) + off);
+                                push_filtered(*reinterpret_cast<const double*>(L + j * 512 + off), U, j, ua, ub, ebase + j * (512u + ((uint32_t)NW << 16)) + off);
                             }
                         } else {
 #pragma unroll
@@ -656,7 +646,7 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                         }
                         else {
                             const uint32_t* uu[1] = {hdr + 4};
-                            heavy_lookup<NW, SEC, 1>((h[0] != 0.0 && valid) ? 1 : 0, h, uu, s, sec, lv, sfilt, e_re, e_im);
+                            heavy_lookup<NW, SEC, 1>((h[0] != 0.0 && valid) ? 1 : 0, h, uu, s, sec, lv, sfilt ? sfilt : gfilt, e_re, e_im);
                         }
                     }
                     p += kBlobHeader + (size_t)n_words * REC_C;

@@ -116,11 +116,13 @@ __global__ void bucket_insert_kernel(HashBucket* buckets, unsigned bmask, int bs
     }
 }
 
-__global__ void filter_build_kernel(uint32_t* filter, const uint64_t* __restrict__ keys, int words, int64_t n, Sector sec) {
+// wide != 0: 128-bit keys — the word comes from the slot hash of both key words (hash_slot), else from the bucket hash
+__global__ void filter_build_kernel(uint32_t* filter, int wshift, const uint64_t* __restrict__ keys, int words, int wide, int64_t n, Sector sec) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !key_in_sector(keys + i * words, words, sec)) return;
+    const unsigned long long k0 = keys[i * words], k1 = wide ? keys[i * words + 1] : 0ull;
     uint32_t w, b1, b2;
-    filter_word_bits(keys[i * words], hash32(keys[i * words], 0ull), w, b1, b2);
+    filter_word_bits(k0, k1, hash32(k0, k1), wshift, w, b1, b2);
     atomicOr(&filter[w], (1u << b1) | (1u << b2));
 }
 
@@ -349,7 +351,27 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
     t->d_dense32_ext = nullptr;
     NAQS_REQUIRE(kind == NAQS_LOOKUP_DENSE || kind == NAQS_LOOKUP_HASH, NAQS_ERR_ARG, "naqs_lookup_build: bad kind");
     const int blocks = (int)((n + 255) / 256);
-    if (kind == NAQS_LOOKUP_DENSE || t->nw32 > 2) t->filter_valid = false;
+    t->filter_valid = false;
+    int rc_f = NAQS_OK;
+    // 2^14 words (the size that fits shared memory; >= 4 bits per key, ~10 % false positives at 2^17 keys) while n <= 2^17;
+    // larger batches get >= 16 bits per key, at most 2^22 words (16 MB, L2-resident)
+    auto build_filter = [&](int wide) -> int {
+        if (n <= 0 || getenv("NAQS_ELOC_NO_FILTER")) return NAQS_OK;
+        int log2w = kFilterLog2WordsSmem;
+        if (4 * n > (32ll << kFilterLog2WordsSmem))
+            while (log2w < kFilterLog2WordsMax && (32ll << log2w) < 16 * n) ++log2w;
+        if (t->filter_alloc_log2w < log2w) {
+            cudaFree(t->d_filter); t->d_filter = nullptr; t->filter_alloc_log2w = -1;
+            NAQS_CUDA(cudaMalloc((void**)&t->d_filter, (size_t)4 << log2w));
+            t->filter_alloc_log2w = log2w;
+        }
+        t->filter_log2w = log2w;
+        NAQS_CUDA(cudaMemsetAsync(t->d_filter, 0, (size_t)4 << log2w, stream));
+        filter_build_kernel<<<blocks, 256, 0, stream>>>(t->d_filter, 32 - log2w, d_keys, t->words, wide, n, t->sector);
+        NAQS_LAUNCHED();
+        t->filter_valid = true;
+        return NAQS_OK;
+    };
     if (kind == NAQS_LOOKUP_DENSE) {
         NAQS_REQUIRE(t->n_qubits <= 30, NAQS_ERR_ARG, "naqs_lookup_build: dense lookup needs n_qubits <= 30");
         const int64_t entries = 1ll << t->n_qubits;
@@ -403,14 +425,7 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
             bucket_insert_kernel<<<blocks, 256, 0, stream>>>(t->d_buckets, lv.bmask, lv.bshift, d_keys, t->words, d_psi, psi_dtype, n, dup_equal ? 1 : 0, t->sector);
             NAQS_LAUNCHED();
         }
-        t->filter_valid = false;
-        if (n > 0 && n * 4 <= (int64_t)kFilterBits && !getenv("NAQS_ELOC_NO_FILTER")) {
-            if (!t->d_filter) NAQS_CUDA(cudaMalloc((void**)&t->d_filter, kFilterBytes));
-            NAQS_CUDA(cudaMemsetAsync(t->d_filter, 0, kFilterBytes, stream));
-            filter_build_kernel<<<blocks, 256, 0, stream>>>(t->d_filter, d_keys, t->words, n, t->sector);
-            NAQS_LAUNCHED();
-            t->filter_valid = true;
-        }
+        if ((rc_f = build_filter(0)) != NAQS_OK) return rc_f;
     } else {
         // load factor <= 0.25 while the table stays well inside L2 (32 B slots), else <= 0.5
         int64_t cap = 1024;
@@ -430,6 +445,7 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
                                                            d_psi, psi_dtype, n, t->sector);
             NAQS_LAUNCHED();
         }
+        if ((rc_f = build_filter(1)) != NAQS_OK) return rc_f;
     }
     t->lookup_kind = kind;
     t->lookup_n = n;
@@ -468,15 +484,16 @@ static int launch_sliced_cfg(naqs_table_t* t, const uint64_t* d_states, const vo
     const bool resident = tiles_per_chunk <= 1;
     const size_t queue_bytes = LK == kLookHash ? (size_t)kQueueCap * 4 * THREADS : 0;
     const size_t queue_offset = resident ? cap : 2 * cap;
-    // the Bloom filter rides along only in the 1-CTA-per-SM shape (it needs 64 KB of shared memory)
-    const bool use_filter = kSlicedFilter[TL] && t->filter_valid;
+    // the Bloom filter is copied to shared memory only in the 1-CTA-per-SM shape (64 KB) and only at its smallest size;
+    // otherwise the kernel consults it in global memory (L2) before a bucket / slot probe
+    const bool use_filter = kSlicedFilter[TL] && t->filter_valid && t->filter_log2w == kFilterLog2WordsSmem;
     const size_t filter_offset = queue_offset + queue_bytes;
     const size_t smem = filter_offset + (use_filter ? kFilterBytes : 0);
     auto kern = eloc_sliced_kernel<NW, NN, THREADS, kSlicedCtasPerSm[TL], LK, SEC, KEYORDER, PSI32>;
     NAQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)(2 * cap + queue_bytes + (kSlicedFilter[TL] ? kFilterBytes : 0))));
     LookupView lv = t->lookup();
-    if (!use_filter) lv.filter = nullptr;
+    lv.filter_in_smem = use_filter ? 1 : 0;
     double2* partial = nullptr;
     uint32_t* need_bits = nullptr;
     if (n_chunks > 1 || KEYORDER) {
