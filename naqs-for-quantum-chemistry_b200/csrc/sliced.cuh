@@ -229,17 +229,11 @@ __device__ __forceinline__ uint32_t parity_word(const unsigned char* __restrict_
 // ------------------------------------------------------------------------------------------ kernel
 constexpr int kLookDense = 0, kLookHash = 1;
 
-// 64-bit address of entry `key` of the dense table with ONE instruction (IMAD.WIDE.U32 on the FMA pipe)
+// 64-bit address of entry `key` of the complex128 dense table (ptxas lowers the wide multiply-add to a LEA pair)
 __device__ __forceinline__ const double2* dense_entry(const double2* __restrict__ base, uint32_t key) {
     unsigned long long addr;
     asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(addr) : "r"(key), "l"(base));
     return reinterpret_cast<const double2*>(addr);
-}
-
-__device__ __forceinline__ const float2* dense_entry32(const float2* __restrict__ base, uint32_t key) {
-    unsigned long long addr;
-    asm("mad.wide.u32 %0, %1, 8, %2;" : "=l"(addr) : "r"(key), "l"(base));
-    return reinterpret_cast<const float2*>(addr);
 }
 
 // complex64 direct-address table whose base is aligned to its size (a power of two): the byte address of entry s ^ u is
@@ -269,33 +263,16 @@ __device__ __forceinline__ void emit_batch32(const double (&h)[B], const uint32_
     }
 }
 
-// Accumulate H[b] * psi_table(s ^ u_b) for a batch of B groups (dense lookup).  All B table reads are issued before any
+// Accumulate H[b] * psi_table(s ^ u_b) for a batch of B groups (dense complex128 table).  All B table reads are issued before any
 // is consumed (memory-level parallelism); lanes whose H is exactly 0.0 (hamiltonian.py:363) or whose coupled
 // state leaves the sector (hamiltonian.py:328) read entry 0 / slot 0 instead — a single broadcast sector —
 // and contribute H * psi = 0 exactly, so no branch is needed.
-template <int NW, bool SEC, bool KEYORDER, bool PSI32, int B>
+template <int NW, bool SEC, bool KEYORDER, int B>
 __device__ __forceinline__ void emit_batch(const double (&h)[B], const uint32_t (&u)[B], const uint32_t (&s)[NW],
                                            bool valid, const Sector& sec, const LookupView& lv, double& e_re, double& e_im) {
     static_assert(NW == 1, "the dense lookup holds keys of <= 30 bits");
     double hh[B];
     double2 p[B];
-    if constexpr (PSI32) {
-        // complex64 table (unique keys): 32 consecutive keys read 256 B = 2 lines per request; float -> double is exact
-        float2 q[B];
-#pragma unroll
-        for (int b = 0; b < B; ++b) {
-            const uint32_t j[1] = {s[0] ^ u[b]};
-            q[b] = __ldg(dense_entry32(lv.dense32, j[0]));
-            hh[b] = h[b];
-            if constexpr (SEC) hh[b] = ((h[b] != 0.0) & valid && in_sector<1>(j, sec)) ? h[b] : 0.0;
-        }
-#pragma unroll
-        for (int b = 0; b < B; ++b) {
-            e_re = __fma_rn(hh[b], (double)q[b].x, e_re);
-            e_im = __fma_rn(hh[b], (double)q[b].y, e_im);
-        }
-        return;
-    }
 #pragma unroll
     for (int b = 0; b < B; ++b) {
         const uint32_t j[1] = {s[0] ^ u[b]};
@@ -555,7 +532,7 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                                 h[jj] = *reinterpret_cast<const double*>(L + j * 128 + off);
                             }
                             if constexpr (PSI32) emit_batch32<SEC, 4>(h, uu[j0 / 4], a0, base_hi, valid, sec8, e_re, e_im);
-                            else emit_batch<NW, SEC, KEYORDER, false, 4>(h, uu[j0 / 4], s, valid, sec, lv, e_re, e_im);
+                            else emit_batch<NW, SEC, KEYORDER, 4>(h, uu[j0 / 4], s, valid, sec, lv, e_re, e_im);
                         }
                     } else {
                         // entry = byte offset of the LUT entry | (flip-mask offset / 4) << 16, both relative to the tile buffer
@@ -596,7 +573,7 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                             h[j] = *reinterpret_cast<const double*>(L + j * 512 + off);
                         }
                         if constexpr (PSI32) emit_batch32<SEC, 5>(h, uu, a0, base_hi, valid, sec8, e_re, e_im);
-                        else emit_batch<NW, SEC, KEYORDER, false, 5>(h, uu, s, valid, sec, lv, e_re, e_im);
+                        else emit_batch<NW, SEC, KEYORDER, 5>(h, uu, s, valid, sec, lv, e_re, e_im);
                     } else {
                         if (sfilt) {  // warp-uniform
                             uint4 ua = make_uint4(0, 0, 0, 0), ub = ua;
@@ -641,7 +618,7 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                                 emit_batch32<SEC, 1>(h, u1, a0, base_hi, valid, sec8, e_re, e_im);
                             } else {
                                 const uint32_t u1[1] = {hdr[4]};
-                                emit_batch<NW, SEC, KEYORDER, false, 1>(h, u1, s, valid, sec, lv, e_re, e_im);
+                                emit_batch<NW, SEC, KEYORDER, 1>(h, u1, s, valid, sec, lv, e_re, e_im);
                             }
                         }
                         else {
@@ -654,6 +631,8 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
             }
         };
 
+        // (measured alternative: per-buffer "empty" mbarriers released warp by warp + prefetch across state blocks instead of the
+        // CTA-wide barrier below — no gain on Li2O, 2 % slower on N2, so the simple form stays)
         if (threadIdx.x == 0 && tile_lo < tile_hi && !(resident && have_resident)) issue(tile_lo, 0);
         for (int t = tile_lo; t < tile_hi; ++t) {
             const int b = resident ? 0 : ((t - tile_lo) & 1);

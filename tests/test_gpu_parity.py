@@ -236,6 +236,56 @@ def test_wide_and_large_synthetic_tables(N, K, M):
     assert np.array_equal(uniq, exp)
 
 
+@pytest.mark.parametrize("N,K,M", [(40, 600, 200_000), (70, 400, 150_000), (30, 900, 300_000)])
+def test_large_batches_with_global_filter(N, K, M):
+    """Batches above 2^17 keys: the Bloom filter no longer fits shared memory and is consulted in L2 before every bucket /
+    slot probe (64-bit bucketed table, 128-bit slot table, and a 32-bit-key table).  The lookup table is the batch plus the
+    coupled states of some rows, so hits and misses both occur; rows are checked against the oracle on a sub-sample."""
+    nb200, c_oracle, eo = _mods()
+    xy, yz, c = eo.synthetic_table(N, K, seed=N + K)
+    st = eo.synthetic_states(N, M, seed=N + 1)
+    psi = eo.synthetic_psi(M, seed=K + 1)
+    t, ct = nb200.DeviceTermTable(xy, yz, c, N), c_oracle.COracleTable(xy, yz, c, N)
+    _, cols, _ = ct.rows(st[:2000])
+    tk = np.unique(np.concatenate([st, cols]), axis=0)
+    tp = eo.synthetic_psi(len(tk), seed=7)
+    assert len(tk) > (1 << 17)
+    e = gpu_eloc(t, st, psi, table_keys=tk, table_psi=tp, kind=nb200._lib.LOOKUP_HASH)
+    sub = np.concatenate([np.arange(1000), np.random.default_rng(3).choice(M, 1000, replace=False)])
+    ref = ct.local_energy(st[sub], psi[sub], tk, tp)
+    assert rel_err(e[sub], ref).max() <= ELOC_RTOL
+    # the filter only removes probes that would miss: identical numbers without it
+    os.environ["NAQS_ELOC_NO_FILTER"] = "1"
+    try:
+        e2 = gpu_eloc(t, st, psi, table_keys=tk, table_psi=tp, kind=nb200._lib.LOOKUP_HASH)
+    finally:
+        del os.environ["NAQS_ELOC_NO_FILTER"]
+    assert np.array_equal(e2, e)
+
+
+def test_caller_owned_dense_table_alignment_and_sector():
+    """naqs_lookup_attach_dense32: the table must be aligned to its size (XOR addressing); out-of-sector keys in a caller-owned
+    table are ignored by the kernel's own sector test (the library's own tables drop them at build time)."""
+    nb200, c_oracle, eo = _mods()
+    from naqs_b200 import distributed as nd
+    t, ct, (N, na, nb) = make_tables("LiH", True)
+    st = random_sector_states(N, na, nb, 200, seed=5)
+    psi = eo.synthetic_psi(len(st), seed=6)
+    stray = np.array([0, 1, 2 ** N - 1], dtype=np.uint64)  # not in the (2, 2) sector
+    keys = torch.from_numpy(np.concatenate([st, stray]).view(np.int64)).cuda()
+    amps = torch.from_numpy(np.concatenate([psi, eo.synthetic_psi(3, seed=9)])).cuda()
+    tbl = nd.aligned_dense_table(t)
+    assert tbl.data_ptr() % (8 << N) == 0
+    nd.allreduce_dense_table(t, keys, amps, out=tbl)   # world size 1: scatter + attach
+    e = nb200._lib.complex_from_pairs(t.local_energy(st, psi, rebuild_lookup=False))
+    assert rel_err(e, ct.local_energy(st, psi)).max() <= ELOC_RTOL
+    raw = torch.empty(((2 << N) + 2, 2), dtype=torch.int32, device="cuda")
+    view = raw[:1 << N] if raw.data_ptr() % (8 << N) else raw[1:(1 << N) + 1]   # a [2^N, 2] view that is NOT aligned to 8 * 2^N bytes
+    assert view.data_ptr() % (8 << N) != 0
+    with pytest.raises(ValueError):
+        t.attach_dense32(view)
+
+
 # ------------------------------------------------------------------------------------------- edge cases
 def test_edge_cases():
     nb200, c_oracle, eo = _mods()
