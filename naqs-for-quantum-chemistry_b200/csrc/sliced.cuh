@@ -310,11 +310,13 @@ __device__ __forceinline__ bool filter_pass(const uint32_t (&j)[NW], const uint3
     return ((word >> b1) & (word >> b2) & 1u) != 0;
 }
 
-// Hash-lookup ("heavy") epilogue of up to B couplings of one thread: sector filter (hamiltonian.py:328), shared-memory
-// Bloom filter when the launch shape carries one, probe of the bucketed table (keys <= 63 bits: one 256-bit load reads
-// the four keys of a 128-byte bucket) or of the 32-byte-slot table (wider keys), complex multiply-add.  Called only for couplings whose H is not exactly 0.0
-// (hamiltonian.py:363), which the per-thread queue of the kernel below makes dense across the warp.  The first probes
-// of all B couplings are issued before any is examined, so their L2 latencies overlap.
+// Hash-lookup ("heavy") epilogue of up to B couplings of one thread: optional Bloom-filter test (`filt`: the filter in
+// global memory when the light path could not consult a shared-memory copy, else nullptr), probe of the bucketed table
+// (keys <= 63 bits: one 256-bit load reads the four keys of a 128-byte bucket) or of the 32-byte-slot table (wider keys),
+// complex multiply-add.  Called for couplings whose H is not exactly 0.0 (hamiltonian.py:363) — and, in the filter shape,
+// whose coupled state passed the filter — which the per-thread queue of the kernel below makes dense across the warp.
+// The first probes of all B couplings are issued before any is examined, so their L2 latencies overlap.  SEC: sector test
+// on the coupled state (hamiltonian.py:328); unused by the library's own tables, which hold in-sector keys only.
 template <int NW, bool SEC, int B>
 __device__ __forceinline__ void heavy_lookup(int n, const double (&h)[B], const uint32_t* const (&u)[B], const uint32_t (&s)[NW],
                                              const Sector& sec, const LookupView& lv, const uint32_t* __restrict__ filt,
