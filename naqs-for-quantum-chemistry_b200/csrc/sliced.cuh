@@ -505,7 +505,7 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                 const uint4 v = reinterpret_cast<const uint4*>(U)[j];
                 k[0] = s[0] ^ v.x; k[1] = s[1] ^ v.y; k[2] = s[2] ^ v.z; k[3] = s[3] ^ v.w;
             }
-            const bool pass = filter_pass<NW>(k, sfilt, lv.filter_wshift);
+            const bool pass = filter_pass<NW>(k, sfilt, 32 - kFilterLog2WordsSmem);  // the shared-memory copy always has 2^14 words
             qtail += (pass && h != 0.0) ? q_adv : 0u;
         };
 
