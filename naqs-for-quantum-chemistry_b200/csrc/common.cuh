@@ -114,6 +114,7 @@ struct LookupView {
     const uint32_t* filter;  // blocked Bloom filter over the table keys (2^(32 - filter_wshift) words) or nullptr
     const float2* dense32;   // [2^N] complex64 copy of the dense table (unique keys + complex64 psi only) or nullptr
     int filter_wshift;       // filter word = hash32 >> filter_wshift
+    const uint32_t* filter_small;  // 2^14-word companion of a larger filter (same hashes, its own word index) or nullptr
     int filter_in_smem;      // the launch copies the filter into shared memory (it has 2^14 words and the shape has room)
 };
 
@@ -195,6 +196,7 @@ struct naqs_table {
     uint32_t* d_filter = nullptr;          // Bloom filter storage (2^filter_log2w words, allocated for filter_alloc_log2w)
     bool filter_valid = false;
     int filter_log2w = naqs::kFilterLog2WordsSmem, filter_alloc_log2w = -1;
+    bool filter_small_valid = false;       // d_filter = [2^14-word companion][2^filter_log2w words] when set
     // generic workspace (scan / sort temporaries, host-path staging)
     void* d_ws = nullptr;
     size_t ws_bytes = 0;
@@ -212,9 +214,9 @@ struct naqs_table {
         for (int64_t c = n_buckets; c > 1; c >>= 1) --bshift;
         return naqs::LookupView{d_dense, d_slots, (unsigned long long)(hash_cap - 1), lookup_kind, shift,
                                 d_buckets, (unsigned)(n_buckets > 0 ? n_buckets - 1 : 0), bshift,
-                                filter_valid ? d_filter : nullptr,
+                                filter_valid ? d_filter + (filter_small_valid ? (1u << naqs::kFilterLog2WordsSmem) : 0u) : nullptr,
                                 dense32_valid ? (d_dense32_ext ? d_dense32_ext : d_dense32) : nullptr,
-                                32 - filter_log2w, 0};
+                                32 - filter_log2w, filter_valid && filter_small_valid ? d_filter : nullptr, 0};
     }
 };
 

@@ -319,7 +319,7 @@ __device__ __forceinline__ bool filter_pass(const uint32_t (&j)[NW], const uint3
 // on the coupled state (hamiltonian.py:328); unused by the library's own tables, which hold in-sector keys only.
 template <int NW, bool SEC, int B>
 __device__ __forceinline__ void heavy_lookup(int n, const double (&h)[B], const uint32_t* const (&u)[B], const uint32_t (&s)[NW],
-                                             const Sector& sec, const LookupView& lv, const uint32_t* __restrict__ filt,
+                                             const Sector& sec, const LookupView& lv, const uint32_t* __restrict__ filt, int filt_wshift,
                                              double& e_re, double& e_im) {
     unsigned long long k0[B], k1[B];
     unsigned slot[B];
@@ -332,7 +332,7 @@ __device__ __forceinline__ void heavy_lookup(int n, const double (&h)[B], const 
         for (int w = 0; w < NW; ++w) j[w] = on[b] ? (s[w] ^ u[b][w]) : s[w];
         if constexpr (SEC) on[b] = on[b] & in_sector<NW>(j, sec);
         key_words64<NW>(j, k0[b], k1[b]);
-        if (filt) on[b] = on[b] & filter_pass<NW>(j, filt, lv.filter_wshift);  // a clear bit proves the key is not in the table
+        if (filt) on[b] = on[b] & filter_pass<NW>(j, filt, filt_wshift);  // a clear bit proves the key is not in the table
         if constexpr (NW <= 2) slot[b] = hash32(k0[b], 0ull) >> lv.bshift;
         else slot[b] = (unsigned)hash_slot(k0[b], k1[b], lv.shift);
     }
@@ -414,9 +414,10 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
     if constexpr (LK == kLookHash) {
         if (lv.filter && lv.filter_in_smem) {
             uint4* dst = reinterpret_cast<uint4*>(smem + filter_offset);
-            const uint4* src = reinterpret_cast<const uint4*>(lv.filter);
+            const uint4* src = reinterpret_cast<const uint4*>(lv.filter_small ? lv.filter_small : lv.filter);
             for (uint32_t i = threadIdx.x; i < kFilterBytes / 16; i += THREADS) dst[i] = __ldg(src + i);
             sfilt = reinterpret_cast<const uint32_t*>(smem + filter_offset);
+            if (lv.filter_small) gfilt = lv.filter;  // the full-size filter screens the survivors once more before a bucket read
         } else {
             gfilt = lv.filter;
         }
@@ -480,7 +481,7 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                 u[b] = reinterpret_cast<const uint32_t*>(buf + (e >> 16) * 4u);
             }
             qtail -= n * QSTRIDE;
-            heavy_lookup<NW, SEC, PB>(n, h, u, s, sec, lv, gfilt, e_re, e_im);  // a shared-memory filter was consulted before queueing
+            heavy_lookup<NW, SEC, PB>(n, h, u, s, sec, lv, gfilt, lv.filter_wshift, e_re, e_im);  // a shared-memory filter was consulted before queueing
         };
         auto drain = [&](const unsigned char* __restrict__ buf) {  // before a tile buffer is released: its offsets die with it
             while (__any_sync(0xffffffffu, qtail != q0)) pop_round(buf);
@@ -625,7 +626,8 @@ eloc_sliced_kernel(SlicedView sv, int tiles_per_chunk, uint32_t buf_bytes, uint3
                         }
                         else {
                             const uint32_t* uu[1] = {hdr + 4};
-                            heavy_lookup<NW, SEC, 1>((h[0] != 0.0 && valid) ? 1 : 0, h, uu, s, sec, lv, sfilt ? sfilt : gfilt, e_re, e_im);
+                            heavy_lookup<NW, SEC, 1>((h[0] != 0.0 && valid) ? 1 : 0, h, uu, s, sec, lv, sfilt ? sfilt : gfilt,
+                                                     sfilt ? 32 - kFilterLog2WordsSmem : lv.filter_wshift, e_re, e_im);
                         }
                     }
                     p += kBlobHeader + (size_t)n_words * REC_C;

@@ -117,13 +117,17 @@ __global__ void bucket_insert_kernel(HashBucket* buckets, unsigned bmask, int bs
 }
 
 // wide != 0: 128-bit keys — the word comes from the slot hash of both key words (hash_slot), else from the bucket hash
-__global__ void filter_build_kernel(uint32_t* filter, int wshift, const uint64_t* __restrict__ keys, int words, int wide, int64_t n, Sector sec) {
+// small != nullptr: also the 2^14-word companion (same bits, word index from the top 14 hash bits)
+__global__ void filter_build_kernel(uint32_t* filter, int wshift, uint32_t* small, const uint64_t* __restrict__ keys, int words, int wide, int64_t n,
+                                    Sector sec) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !key_in_sector(keys + i * words, words, sec)) return;
     const unsigned long long k0 = keys[i * words], k1 = wide ? keys[i * words + 1] : 0ull;
+    const uint32_t h = hash32(k0, k1);
     uint32_t w, b1, b2;
-    filter_word_bits(k0, k1, hash32(k0, k1), wshift, w, b1, b2);
+    filter_word_bits(k0, k1, h, wshift, w, b1, b2);
     atomicOr(&filter[w], (1u << b1) | (1u << b2));
+    if (small) atomicOr(&small[h >> (32 - kFilterLog2WordsSmem)], (1u << b1) | (1u << b2));
 }
 
 __global__ void widen_keys_kernel(const void* __restrict__ in, int itemsize, int64_t n, uint64_t* __restrict__ out) {
@@ -354,20 +358,24 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
     t->filter_valid = false;
     int rc_f = NAQS_OK;
     // 2^14 words (the size that fits shared memory; >= 4 bits per key, ~10 % false positives at 2^17 keys) while n <= 2^17;
-    // larger batches get >= 16 bits per key, at most 2^22 words (16 MB, L2-resident)
+    // larger batches get >= 16 bits per key, at most 2^22 words (16 MB, L2-resident) — and, up to 2.5 * 2^17 keys, a 2^14-word
+    // companion for shared memory that still rejects more than half of the misses before anything is queued
     auto build_filter = [&](int wide) -> int {
         if (n <= 0 || getenv("NAQS_ELOC_NO_FILTER")) return NAQS_OK;
         int log2w = kFilterLog2WordsSmem;
         if (4 * n > (32ll << kFilterLog2WordsSmem))
             while (log2w < kFilterLog2WordsMax && (32ll << log2w) < 16 * n) ++log2w;
+        const bool small = log2w > kFilterLog2WordsSmem && 2 * n <= (5ll << 17);
         if (t->filter_alloc_log2w < log2w) {
             cudaFree(t->d_filter); t->d_filter = nullptr; t->filter_alloc_log2w = -1;
-            NAQS_CUDA(cudaMalloc((void**)&t->d_filter, (size_t)4 << log2w));
+            NAQS_CUDA(cudaMalloc((void**)&t->d_filter, ((size_t)4 << log2w) + kFilterBytes));
             t->filter_alloc_log2w = log2w;
         }
         t->filter_log2w = log2w;
-        NAQS_CUDA(cudaMemsetAsync(t->d_filter, 0, (size_t)4 << log2w, stream));
-        filter_build_kernel<<<blocks, 256, 0, stream>>>(t->d_filter, 32 - log2w, d_keys, t->words, wide, n, t->sector);
+        t->filter_small_valid = small;
+        uint32_t* big = t->d_filter + (small ? (1u << kFilterLog2WordsSmem) : 0u);
+        NAQS_CUDA(cudaMemsetAsync(t->d_filter, 0, ((size_t)4 << log2w) + (small ? kFilterBytes : 0), stream));
+        filter_build_kernel<<<blocks, 256, 0, stream>>>(big, 32 - log2w, small ? t->d_filter : nullptr, d_keys, t->words, wide, n, t->sector);
         NAQS_LAUNCHED();
         t->filter_valid = true;
         return NAQS_OK;
@@ -486,7 +494,7 @@ static int launch_sliced_cfg(naqs_table_t* t, const uint64_t* d_states, const vo
     const size_t queue_offset = resident ? cap : 2 * cap;
     // the Bloom filter is copied to shared memory only in the 1-CTA-per-SM shape (64 KB) and only at its smallest size;
     // otherwise the kernel consults it in global memory (L2) before a bucket / slot probe
-    const bool use_filter = kSlicedFilter[TL] && t->filter_valid && t->filter_log2w == kFilterLog2WordsSmem;
+    const bool use_filter = kSlicedFilter[TL] && t->filter_valid && (t->filter_log2w == kFilterLog2WordsSmem || t->filter_small_valid);
     const size_t filter_offset = queue_offset + queue_bytes;
     const size_t smem = filter_offset + (use_filter ? kFilterBytes : 0);
     auto kern = eloc_sliced_kernel<NW, NN, THREADS, kSlicedCtasPerSm[TL], LK, SEC, KEYORDER, PSI32>;
