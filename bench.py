@@ -341,6 +341,7 @@ def main():
     ap.add_argument("--synthetic", type=int, nargs=3, default=[64, 10000, 100000], metavar=("N", "K", "M"))
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="states of the bounded cpu_baseline sample (0 = skip)")
     ap.add_argument("--ref-sample", type=int, default=50_000, help="states per step of --impl reference")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: ONE batch of M states (seed 0) split across the ranks (default: weak, M per rank)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs and the LiH call-latency leg")
     args = ap.parse_args()
@@ -365,7 +366,13 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    wl = make_workload(args.workload, rank, m_override=args.states, synth=tuple(args.synthetic))
+    wl = make_workload(args.workload, 0 if args.strong else rank, m_override=args.states, synth=tuple(args.synthetic))
+    if args.strong and world > 1:  # every rank generated the same batch; keep this rank's contiguous block of rows
+        lo, hi = naqs_b200.distributed.shard_bounds(len(wl["states"]), world, rank)
+        if (hi - lo) * world != len(wl["states"]):
+            raise SystemExit("--strong needs a batch size divisible by the number of ranks")
+        wl["states"], wl["psi"] = wl["states"][lo:hi], wl["psi"][lo:hi]
+        wl["desc"] += f" — STRONG scaling: the batch is split over {world} ranks"
     table = naqs_b200.DeviceTermTable(wl["xy"], wl["yz"], wl["c"], wl["N"], wl["na"], wl["nb"], device=dev)
     M, K, W = len(wl["states"]), table.K, table.words
     h_states = torch.from_numpy(np.ascontiguousarray(wl["states"]).reshape(M, W).view(np.int64)).pin_memory()
@@ -524,7 +531,7 @@ def main():
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": wl["desc"], "states_per_gpu": M, "terms": K, "lookup_keys": T,
                        "parallelism": f"states sharded x{world}, Pauli table replicated" + ((", NCCL all-reduce (MAX) of the 2^N-entry complex64 amplitude table" if allreduce_table else ", NCCL all-gather of (key, psi)") + " + all-reduce of 5 fp64 sums" if world > 1 else ""),

@@ -13,6 +13,7 @@
 
 #include <atomic>
 #include <string>
+#include <vector>
 
 #include "../../include/naqs_eloc.h"
 
@@ -72,6 +73,12 @@ struct TableView {
     const uint32_t* gstart;  // [G+1]       term offsets of each group
     int K, G;
     int f32;                 // 1: every partial sum of H_ij is rounded to float32 (the reference's dtype=np.float32 kernel)
+};
+
+// Table chunks of a sliced launch (grid.y): chunk c walks tiles [lo[c], lo[c + 1]) — contiguous ranges of about equal WORK.
+constexpr int kMaxChunks = 16;
+struct ChunkBounds {
+    int lo[kMaxChunks + 1];
 };
 
 // A shared-memory tile of the term table: terms [t0, t1) and the groups touching them [g0, g1).
@@ -176,6 +183,7 @@ struct naqs_table {
     size_t stream_bytes = 0;
     void* d_stiles[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [0..2] dense, [3..5] hash tile lists
     int n_stiles[6] = {0, 0, 0, 0, 0, 0};
+    std::vector<uint32_t> stile_cost[6];   // host: estimated work per tile (group-equivalents), for balanced table chunks
     int nn = 0;
     double2* d_partial = nullptr;
     size_t partial_bytes = 0;

@@ -314,7 +314,16 @@ int naqs_table_create(naqs_table_t** out, const uint64_t* h_xy, const uint64_t* 
         naqs_table_destroy(t);
         return rc;
     }
-    for (int c = 0; c < 6; ++c) t->n_stiles[c] = (int)stiles[c].size();
+    for (int c = 0; c < 6; ++c) {
+        t->n_stiles[c] = (int)stiles[c].size();
+        // work estimate per tile in (state, group) pairs: 8 / 5 groups per A / B record, a big-group word ~ 1.5, a blob ~ 3
+        const size_t rc = rec_bytes_C(sh.nn);
+        for (const STile& tl : stiles[c]) {
+            uint32_t cost = tl.kind == kSecA ? 8u * tl.count + 1u : tl.kind == kSecB ? 5u * tl.count + 1u
+                                             : (uint32_t)(3u * tl.count + 3u * ((tl.bytes - kBlobHeader * tl.count) / rc) / 2u + 1u);
+            t->stile_cost[c].push_back(cost);
+        }
+    }
     if (cudaStreamCreateWithFlags(&t->own_stream, cudaStreamNonBlocking) != cudaSuccess) t->own_stream = nullptr;
     *out = t;
     return NAQS_OK;
@@ -486,10 +495,28 @@ static int launch_sliced_cfg(naqs_table_t* t, const uint64_t* d_states, const vo
     constexpr int TL = CFG + (LK == kLookHash ? 3 : 0);  // launch shape / tile list
     constexpr int THREADS = kSlicedThreads[TL];
     const int n_tiles = t->n_stiles[TL];
-    const int tiles_per_chunk = std::max(1, (n_tiles + n_chunks - 1) / n_chunks);
-    n_chunks = std::max(1, (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk);
+    // table chunks (grid.y): contiguous tile ranges of about equal estimated work — with at most one wave of CTAs the launch
+    // lasts as long as its heaviest chunk, and A tiles (8 groups per 1.4 KB) are far heavier per byte than big-group tiles
+    n_chunks = std::max(1, std::min(std::min(n_chunks, kMaxChunks), std::max(n_tiles, 1)));
+    ChunkBounds cb;
+    {
+        const std::vector<uint32_t>& cost = t->stile_cost[TL];
+        uint64_t total = 0, run = 0;
+        for (uint32_t c : cost) total += c;
+        int c = 0;
+        cb.lo[0] = 0;
+        for (int i = 0; i < n_tiles; ++i) {
+            // close chunk c before tile i once it has its share, keeping enough tiles for the chunks that follow
+            if (c + 1 < n_chunks && i > cb.lo[c] && (run * n_chunks >= total * (uint64_t)(c + 1) || n_tiles - i <= n_chunks - 1 - c)) cb.lo[++c] = i;
+            run += cost[(size_t)i];
+        }
+        while (c < n_chunks) cb.lo[++c] = n_tiles;
+        for (int k = n_chunks + 1; k <= kMaxChunks; ++k) cb.lo[k] = n_tiles;
+    }
+    int max_chunk_tiles = 0;
+    for (int c = 0; c < n_chunks; ++c) max_chunk_tiles = std::max(max_chunk_tiles, cb.lo[c + 1] - cb.lo[c]);
     const size_t cap = kSlicedCap[TL];
-    const bool resident = tiles_per_chunk <= 1;
+    const bool resident = max_chunk_tiles <= 1;
     const size_t queue_bytes = LK == kLookHash ? (size_t)kQueueCap * 4 * THREADS : 0;
     const size_t queue_offset = resident ? cap : 2 * cap;
     // the Bloom filter is copied to shared memory only in the 1-CTA-per-SM shape (64 KB) and only at its smallest size;
@@ -524,7 +551,7 @@ static int launch_sliced_cfg(naqs_table_t* t, const uint64_t* d_states, const vo
     const int slots = sm_count * kSlicedCtasPerSm[TL];
     dim3 grid((unsigned)std::min<int64_t>(n_blocks, slots), (unsigned)n_chunks);
     SlicedView sv{t->d_stream, (const STile*)t->d_stiles[TL], n_tiles, t->nn};
-    kern<<<grid, THREADS, smem, stream>>>(sv, tiles_per_chunk, (uint32_t)cap, (uint32_t)queue_offset, (uint32_t)filter_offset, t->sector, lv, d_states, need_bits, d_psi, psi_dtype,
+    kern<<<grid, THREADS, smem, stream>>>(sv, cb, (uint32_t)cap, (uint32_t)queue_offset, (uint32_t)filter_offset, t->sector, lv, d_states, need_bits, d_psi, psi_dtype,
                                           M, reinterpret_cast<double2*>(d_eloc), partial);
     NAQS_LAUNCHED();
     if (KEYORDER) {
