@@ -316,11 +316,14 @@ int naqs_table_create(naqs_table_t** out, const uint64_t* h_xy, const uint64_t* 
     }
     for (int c = 0; c < 6; ++c) {
         t->n_stiles[c] = (int)stiles[c].size();
-        // work estimate per tile in (state, group) pairs: 8 / 5 groups per A / B record, a big-group word ~ 1.5, a blob ~ 3
+        // work estimate per tile in (state, group) pairs: 8 / 5 groups per A / B record, a big-group word ~ 1.5; a blob ends in
+        // one un-batched lookup per state: cheap against the dense table or a shared-memory filter, two dependent global
+        // reads (filter word, bucket) in the hash shapes without one
         const size_t rc = rec_bytes_C(sh.nn);
+        const uint32_t blob_cost = c < 3 ? 2u : (kSlicedFilter[c] ? 4u : 12u);
         for (const STile& tl : stiles[c]) {
             uint32_t cost = tl.kind == kSecA ? 8u * tl.count + 1u : tl.kind == kSecB ? 5u * tl.count + 1u
-                                             : (uint32_t)(3u * tl.count + 3u * ((tl.bytes - kBlobHeader * tl.count) / rc) / 2u + 1u);
+                                             : (uint32_t)(blob_cost * tl.count + 3u * ((tl.bytes - kBlobHeader * tl.count) / rc) / 2u + 1u);
             t->stile_cost[c].push_back(cost);
         }
     }
