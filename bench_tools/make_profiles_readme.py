@@ -60,6 +60,18 @@ for g in (1, 2, 4, 8):
         d = last_json(fn)
         base = base or d["value"]
         w(f"| {g} | {d['value']:.3e} | {d['ms_per_step']:.3f} | {d['roofline']['kernel_ms']:.3f} | {100 * d['value'] / (g * base):.0f}% |")
+for tag, title in (("scale_li2o", "Li2O weak scaling (10^5 sector states per GPU, hash lookup, all-gather exchange; the lookup table grows with the rank count)"),
+                   ("strong_li2o", "Li2O strong scaling (`bench.py --strong`: ONE batch of 10^5 states split over the ranks)")):
+    rows_ = []
+    for g in (1, 2, 4, 8):
+        fn = f"{R}_{tag}_g{g}.json"
+        if os.path.exists(os.path.join(P, fn)):
+            d = last_json(fn)
+            rows_.append(f"| {g} | {d['value']:.3e} | {d['ms_per_step']:.3f} | {d['roofline']['kernel_ms']:.3f} |")
+    if rows_:
+        w(f"\n{title} (`{R}_{tag}_g*.json`):\n")
+        w("| GPUs | value (couplings/s) | ms/step | kernel ms |\n|---|---|---|---|")
+        out.extend(rows_)
 w(f"\n`{R}_collective_probe_g2.json`: NCCL all-reduce latencies at this size against torch's symmetric-memory kernels (why the exchange stays on NCCL).\n")
 w("## Other files")
 w(f"`pipe_peaks_{R}.json` — measured POPC / LOP3 / IMAD / DADD / gather ceilings (`bench_tools/pipe_peaks.cu`);\n`{R}_sanitize_*.log` — compute-sanitizer memcheck + racecheck: 0 errors, 0 hazards;\n"
