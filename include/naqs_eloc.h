@@ -84,7 +84,11 @@ int naqs_table_info(const naqs_table_t* t, int64_t* info8);
  * that the reference performs with scipy fancy indexing H[idx[:,None], idx]
  * (src/optimizer/hamiltonian.py:93-111 get_H; or the merge-join of src_cpp/sparse_math.pyx:316-342).
  * Builds, on `stream`, an internal device structure from T (key, psi) pairs.  Duplicate keys are
- * summed, as scipy's repeated column would be.  The table stays valid until the next build. */
+ * summed, as scipy's repeated column would be.  The table stays valid until the next build.
+ * With a sector (n_alpha / n_beta >= 0) only keys inside it are stored: a coupled state outside the sector then never
+ * matches, which is the reference's sector filter on coupled states (hamiltonian.py:321-328) applied once per table key;
+ * a stray out-of-sector key in the batch is ignored exactly as the reference ignores it.  Hash lookups also get a
+ * Bloom filter over the stored keys (shared memory up to 2^17 keys, L2-resident above). */
 int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi, int psi_dtype,
                       int64_t n_keys, int kind, void* stream);
 
