@@ -69,6 +69,14 @@ def sector_states(N, na, nb, m, seed):
     return rng.permutation(a)[:m].astype(np.uint64)
 
 
+def full_sector(N, na, nb):
+    """Every key with na bits on even and nb bits on odd qubits (small sectors only), ascending."""
+    import itertools
+    ev = [sum(1 << q for q in c) for c in itertools.combinations(range(0, N, 2), na)]
+    od = [sum(1 << q for q in c) for c in itertools.combinations(range(1, N, 2), nb)]
+    return np.sort(np.array([a | b for a in ev for b in od], dtype=np.uint64))
+
+
 def synthetic_table(N, K, seed=0):
     """Random Pauli sum of SURVEY.md §8d config 5: 2-/4-qubit flip masks shared by ~6 terms each (+ a diagonal group),
     YZ masks = JW-like contiguous run XOR a random weight-N/4 mask, normal fp64 coefficients."""
@@ -326,6 +334,37 @@ def measure_extras(naqs_b200, dev, args):
     except Exception as e:  # noqa: BLE001
         lih["reference_cpu"] = f"unavailable: {e}"
     out["lih_vmc_eloc_call"] = lih
+    # CSR-rows mode (the update_H replacement: stored couplings with restricted column indices, bit-exact matrix elements):
+    # the full N2 sector (14 400 states -> 1.3 M stored elements), device result in device memory vs the reference's update_H
+    try:
+        xy, yz, c, N, na, nb = load_table("N2")
+        sec = full_sector(N, na, nb)
+        table = naqs_b200.DeviceTermTable(xy, yz, c, N, na, nb, device=dev)
+        d_sec = torch.from_numpy(sec.view(np.int64)).to(dev).reshape(-1, 1)
+        for _ in range(3):
+            indptr, _, _, _ = table.rows(d_sec)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            indptr, cols, ridx, vals = table.rows(d_sec)
+        torch.cuda.synchronize()
+        rows_ms = 1e3 * (time.perf_counter() - t0) / 10
+        rows = {"states": int(len(sec)), "nnz": int(indptr[-1].item()), "b200_rows_ms": rows_ms}
+        try:
+            from oracle import ref_path
+            path = ref_path.ReferencePath(xy, yz, c, N, na, nb)
+            best = 1e30
+            for _ in range(2):
+                path.reset()
+                t0 = time.perf_counter()
+                H = path.update_H(sec.astype(np.int64), check_unseen=False, assume_unique=True)
+                best = min(best, time.perf_counter() - t0)
+            rows.update({"reference_cpu_update_H_ms": 1e3 * best, "reference_nnz": int(H.nnz), "cores": os.cpu_count()})
+        except Exception as e:  # noqa: BLE001
+            rows["reference_cpu"] = f"unavailable: {e}"
+        out["n2_sector_csr_rows"] = rows
+    except Exception as e:  # noqa: BLE001
+        out["n2_sector_csr_rows"] = {"error": repr(e)}
     return out
 
 

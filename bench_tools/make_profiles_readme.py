@@ -29,7 +29,9 @@ if oc:
     w(f"Other BASELINE configs from the same run (`other_configs`): H2O 1e5 rows {h.get('value', 0):.3e} ({1e3 * h.get('ms_per_step', 0):.0f} us/step), "
       f"Li2O 1e5 sector states {l.get('value', 0):.3e} ({l.get('ms_per_step', 0):.3f} ms/step); LiH VMC E_loc call ({v.get('states')} states): "
       f"B200 host call {1e3 * v.get('b200_host_call_ms', 0):.0f} us vs reference CPU {1e3 * v.get('reference_cpu_cold_cache_ms', 0):.0f} us (cold H cache) / "
-      f"{1e3 * v.get('reference_cpu_warm_cache_ms', 0):.0f} us (warm).\n")
+      f"{1e3 * v.get('reference_cpu_warm_cache_ms', 0):.0f} us (warm)."
+      + (f" CSR rows of the full N2 sector ({oc['n2_sector_csr_rows'].get('nnz')} stored elements): {oc['n2_sector_csr_rows'].get('b200_rows_ms', 0):.2f} ms vs reference update_H "
+         f"{oc['n2_sector_csr_rows'].get('reference_cpu_update_H_ms', 0):.0f} ms." if "n2_sector_csr_rows" in oc and "nnz" in oc["n2_sector_csr_rows"] else "") + "\n")
 n, l = ncu["n2_1e6"], ncu["li2o_1e5"]
 w(f"## Hot kernel, `ncu --set full --clock-control none` (`{R}_final_n2_ncu_raw.csv`, `{R}_final_li2o_ncu_raw.csv`; summary `ncu_summary_{R}.json`)\n")
 w("| metric | N2 1e6 (key-order walk, dense complex64 table) | Li2O 1e5 (hash lookup, Bloom filter in shared memory, survivor queue) |\n|---|---|---|")
