@@ -75,6 +75,13 @@ for tag, title in (("scale_li2o", "Li2O weak scaling (10^5 sector states per GPU
         w("| GPUs | value (couplings/s) | ms/step | kernel ms |\n|---|---|---|---|")
         out.extend(rows_)
 w(f"\n`{R}_collective_probe_g2.json`: NCCL all-reduce latencies at this size against torch's symmetric-memory kernels (why the exchange stays on NCCL).\n")
+rl = os.path.join(P, f"{R}_bench_n2_1e6_rows_leg.json")
+if os.path.exists(rl):
+    r_ = last_json(f"{R}_bench_n2_1e6_rows_leg.json")["other_configs"].get("n2_sector_csr_rows", {})
+    if "nnz" in r_:
+        w(f"## CSR-rows mode (`{R}_bench_n2_1e6_rows_leg.json`, `other_configs.n2_sector_csr_rows`)\n")
+        w(f"Full N2 sector, {r_['states']} states -> {r_['nnz']} stored matrix elements (same count as the reference): device rows "
+          f"(count + scan + fill with restricted column indices) {r_['b200_rows_ms']:.2f} ms vs reference `update_H` {r_['reference_cpu_update_H_ms']:.0f} ms on {r_['cores']} cores.\n")
 w("## Other files")
 w(f"`pipe_peaks_{R}.json` — measured POPC / LOP3 / IMAD / DADD / gather ceilings (`bench_tools/pipe_peaks.cu`);\n`{R}_sanitize_*.log` — compute-sanitizer memcheck + racecheck: 0 errors, 0 hazards;\n"
   f"`{R}_v1_*` — the first (direct, POPC-bound) kernel for comparison: 1.59e12 couplings/s, 1.37 ms kernel.\n")
