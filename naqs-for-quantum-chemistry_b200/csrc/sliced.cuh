@@ -393,7 +393,7 @@ constexpr int kQueueCap = 16;  // pending couplings per thread (hash mode)
 // read of a group falls into one aligned 512-byte block: 4 L1 lines per request instead of ~11 scattered sectors.
 template <int NW, int NN, int THREADS, int CTAS_PER_SM, int LK, bool SEC, bool KEYORDER, bool PSI32>
 __global__ void __launch_bounds__(THREADS, CTAS_PER_SM)
-eloc_sliced_kernel(SlicedView sv, ChunkBounds chunks, uint32_t buf_bytes, uint32_t queue_offset, uint32_t filter_offset, Sector sec, LookupView lv,
+eloc_sliced_kernel(SlicedView sv, const __grid_constant__ ChunkBounds chunks, uint32_t buf_bytes, uint32_t queue_offset, uint32_t filter_offset, Sector sec, LookupView lv,
                    const uint64_t* __restrict__ states, const uint32_t* __restrict__ need, const void* __restrict__ psi,
                    int psi_dtype, int64_t M, double2* __restrict__ out, double2* __restrict__ partial) {
     extern __shared__ __align__(128) unsigned char smem[];
