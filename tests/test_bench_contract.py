@@ -41,3 +41,22 @@ def test_b200_arm_fails_loudly_without_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3", "--cpu-sample", "0"],
                        capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode != 0 and not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_bench_helpers():
+    """Workload helpers of bench.py that the extras / --strong legs rely on (no GPU)."""
+    import importlib.util
+    import numpy as np
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    sec = b.full_sector(12, 2, 2)                       # LiH: C(6,2)^2 = 225 states (hilbert.py:446-449)
+    assert len(sec) == 225 and len(np.unique(sec)) == 225
+    even = sum(1 << q for q in range(0, 12, 2))
+    assert all(bin(int(k) & even).count("1") == 2 and bin(int(k) & (even << 1)).count("1") == 2 for k in sec)
+    st = b.sector_states(30, 7, 7, 1000, 3)            # random distinct Li2O sector states
+    assert len(st) == 1000 and len(np.unique(st)) == 1000
+    ev30 = sum(1 << q for q in range(0, 30, 2))
+    assert all(bin(int(k) & ev30).count("1") == 7 and bin(int(k) & (ev30 << 1)).count("1") == 7 for k in st[:50])
+    xy, yz, c = b.synthetic_table(70, 120)
+    assert xy.shape == (120, 2) and yz.shape == (120, 2) and c.shape == (120,)
