@@ -375,7 +375,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="n2_1e6")
+    ap.add_argument("--workload", default=os.environ.get("BENCH_WL", "n2_1e6"))
     ap.add_argument("--states", type=int, default=None, help="override M (states per GPU)")
     ap.add_argument("--synthetic", type=int, nargs=3, default=[64, 10000, 100000], metavar=("N", "K", "M"))
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="states of the bounded cpu_baseline sample (0 = skip)")

@@ -81,6 +81,30 @@ struct ChunkBounds {
     int lo[kMaxChunks + 1];
 };
 
+// Key-order kernel (keyorder.cuh): one unit per parity word of its stream, chunk descriptors passed by value, cached launch plan
+struct KoUnit {
+    uint32_t kind;      // kSecA / kSecB / kSecC
+    uint32_t bytes;
+    uint32_t cost;      // estimated work (group-equivalents), for balanced chunks
+    uint32_t last;      // C: last word of its blob (a chunk may only end after one)
+};
+struct KoChunk {
+    uint32_t off, bytes;       // byte range in the stream (multiples of 16)
+    uint32_t n_a, n_b, n_c;    // A records, B records, C words
+    uint32_t off_b, off_c;     // byte offsets of the first B record / C word relative to `off`
+    uint32_t r0, n_words;      // first parity word (index into HT) and their number (= n_a + n_b + n_c)
+};
+struct KoChunks {
+    KoChunk c[kMaxChunks];
+};
+struct KoPlan {
+    int valid = 0;           // 0 = not planned yet, 1 = usable, -1 = the key-order kernel cannot run this table
+    int shape = 0;           // 0: 1024 x 1 CTA/SM, 1: 512 x 2, 2: 256 x 4
+    int n_chunks = 1, grid_x = 1;
+    uint32_t smem = 0, tw_offset = 0, tw_stride = 0;
+    KoChunks chunks{};
+};
+
 // A shared-memory tile of the term table: terms [t0, t1) and the groups touching them [g0, g1).
 // A group may straddle two tiles; its partial sum is carried in registers.
 struct Tile {
@@ -185,6 +209,15 @@ struct naqs_table {
     int n_stiles[6] = {0, 0, 0, 0, 0, 0};
     std::vector<uint32_t> stile_cost[6];   // host: estimated work per tile (group-equivalents), for balanced table chunks
     int nn = 0;
+    // key-order (v3) stream: single-word keys, n_qubits in [5, 26] (keyorder.cuh); the host copy of its unit list drives the chunking
+    unsigned char* d_ko_stream = nullptr;
+    size_t ko_stream_bytes = 0;
+    uint32_t* d_ko_ht = nullptr;
+    int ko_n_hi = 0, ko_r_total_pad = 0;
+    std::vector<naqs::KoUnit> ko_units;
+    bool env_no_keyorder = false, env_no_dense32 = false, env_no_filter = false;  // A/B switches, read once at table creation
+    bool ko_disabled = false;          // NAQS_ELOC_NO_KO3 (A/B against the generic key-order walk of sliced.cuh)
+    naqs::KoPlan ko_plan{};            // cached launch plan (the key space, hence the shape, is fixed per table)
     double2* d_partial = nullptr;
     size_t partial_bytes = 0;
     // lookup

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "eloc_kernels.cuh"
 #include "sliced.cuh"
+#include "keyorder.cuh"
 
 namespace naqs {
 
@@ -170,6 +171,7 @@ constexpr int kSlicedCtasPerSm[6] = {1, 2, 4, 1, 2, 4};
 constexpr bool kSlicedFilter[6] = {false, false, false, true, false, false};
 constexpr size_t kSlicedCap[6] = {112640, 55296, 26624, 47104, 36864, 18432};  // [3]: 2 x 46 KB tiles + 64 KB queue + 64 KB filter
 constexpr size_t kSlicedMaxBlob = 16384;
+constexpr size_t kKoMaxBlobWords = 5;  // key-order stream: parity words (30 terms each) of a big group multiplied by psi together
 static_assert(kSlicedCap[3] < 65536 && kSlicedCap[4] < 65536 && kSlicedCap[5] < 65536, "queue entries of the hash shapes hold 16-bit byte offsets into a tile");
 
 static int tile_cap_for(int nw32, int64_t K) {
@@ -288,10 +290,30 @@ int naqs_table_create(naqs_table_t** out, const uint64_t* h_xy, const uint64_t* 
         t->nn = sh.nn;
         t->stream_bytes = sh.stream.size();
     }
+    KoHost kh;
+    const bool have_ko = NW == 1 && n_qubits >= 5 && n_qubits <= 26 && K > 0;
+    if (have_ko) {
+        std::vector<HostGroup> hg((size_t)G);
+        for (int64_t g = 0; g < G; ++g) {
+            HostGroup& x = hg[(size_t)g];
+            for (int w = 0; w < 4; ++w) x.u[w] = w < NW ? gxy[(size_t)w * G + g] : 0u;
+            const uint32_t b = gstart[(size_t)g], e = gstart[(size_t)g + 1];
+            x.yz.assign(yz.begin() + b, yz.begin() + e);
+            x.c.assign(coeff.begin() + b, coeff.begin() + e);
+        }
+        build_ko_host(hg, n_qubits, kKoMaxBlobWords, kh);
+        t->ko_n_hi = kh.n_hi; t->ko_r_total_pad = kh.r_total_pad; t->ko_stream_bytes = kh.stream.size();
+        t->ko_units = kh.units;
+    }
     t->coeff_f32_exact = true;
     for (int64_t k = 0; k < K; ++k) t->coeff_f32_exact = t->coeff_f32_exact && ((double)(float)h_coeff[k] == h_coeff[k] || h_coeff[k] != h_coeff[k]);
+    // environment switches (A/B measurements) are read once, here — never on the launch path
     const char* algo_env = getenv("NAQS_ELOC_ALGO");
     t->algo = (algo_env && std::string(algo_env) == "direct") ? 1 : 0;
+    t->env_no_keyorder = getenv("NAQS_ELOC_NO_KEYORDER") != nullptr;
+    t->env_no_dense32 = getenv("NAQS_ELOC_NO_DENSE32") != nullptr;
+    t->env_no_filter = getenv("NAQS_ELOC_NO_FILTER") != nullptr;
+    t->ko_disabled = getenv("NAQS_ELOC_NO_KO3") != nullptr;
 
     int rc = NAQS_OK;
     auto upload = [&](void** dptr, const void* src, size_t bytes) -> int {
@@ -310,7 +332,9 @@ int naqs_table_create(naqs_table_t** out, const uint64_t* h_xy, const uint64_t* 
         (rc = upload(&t->d_stiles[2], stiles[2].data(), stiles[2].size() * sizeof(STile))) ||
         (rc = upload(&t->d_stiles[3], stiles[3].data(), stiles[3].size() * sizeof(STile))) ||
         (rc = upload(&t->d_stiles[4], stiles[4].data(), stiles[4].size() * sizeof(STile))) ||
-        (rc = upload(&t->d_stiles[5], stiles[5].data(), stiles[5].size() * sizeof(STile)))) {
+        (rc = upload(&t->d_stiles[5], stiles[5].data(), stiles[5].size() * sizeof(STile))) ||
+        (have_ko && ((rc = upload((void**)&t->d_ko_stream, kh.stream.data(), kh.stream.size())) ||
+                     (rc = upload((void**)&t->d_ko_ht, kh.ht.data(), kh.ht.size() * 4))))) {
         naqs_table_destroy(t);
         return rc;
     }
@@ -341,6 +365,7 @@ int naqs_table_destroy(naqs_table_t* t) {
     if (t->own_stream) cudaStreamDestroy(t->own_stream);
     cudaFree(t->d_tiles); cudaFree(t->d_binom); cudaFree(t->d_stream); cudaFree(t->d_partial);
     for (int c = 0; c < 6; ++c) cudaFree(t->d_stiles[c]);
+    cudaFree(t->d_ko_stream); cudaFree(t->d_ko_ht);
     delete t;
     return NAQS_OK;
 }
@@ -373,7 +398,7 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
     // larger batches get >= 16 bits per key, at most 2^22 words (16 MB, L2-resident) — and, up to 2.5 * 2^17 keys, a 2^14-word
     // companion for shared memory that still rejects more than half of the misses before anything is queued
     auto build_filter = [&](int wide) -> int {
-        if (n <= 0 || getenv("NAQS_ELOC_NO_FILTER")) return NAQS_OK;
+        if (n <= 0 || t->env_no_filter) return NAQS_OK;
         int log2w = kFilterLog2WordsSmem;
         if (4 * n > (32ll << kFilterLog2WordsSmem))
             while (log2w < kFilterLog2WordsMax && (32ll << log2w) < 16 * n) ++log2w;
@@ -403,7 +428,7 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
         // key-order walk + unique complex64 amplitudes: an 8-byte-per-entry table suffices (exact: the kernel widens
         // float -> double, as sparse_math.pyx:33-37 does); otherwise the complex128 table with duplicate summation
         const bool use32 = assume_unique && psi_dtype == NAQS_C64 && t->algo == 0 && n >= entries / 8 && t->n_qubits <= 26 &&
-                           !getenv("NAQS_ELOC_NO_KEYORDER") && !getenv("NAQS_ELOC_NO_DENSE32");
+                           !t->env_no_keyorder && !t->env_no_dense32;
         if (use32) {
             if (t->dense32_entries < entries) {
                 // the kernel forms entry addresses as (base ^ key * 8) ^ (u * 8) (emit_batch32): base aligned to the table size
@@ -569,6 +594,135 @@ static int launch_sliced_cfg(naqs_table_t* t, const uint64_t* d_states, const vo
     return NAQS_OK;
 }
 
+// ------------------------------------------------------------------------------------------ key-order kernel (keyorder.cuh)
+constexpr int kKoThreads[3] = {1024, 512, 256};
+constexpr int kKoCtasPerSm[3] = {1, 2, 4};
+// dynamic shared memory available to one CTA when `ctas` of them share an SM (228 KB per SM, 1 KB reserved per CTA, 128 B static)
+// (static = the mbarrier, padded to the 128-byte alignment of the dynamic window: cuobjdump reports SHARED:1152 = 1024 reserved + 128)
+static size_t ko_smem_cap(int ctas) { return ctas == 1 ? (size_t)232448 - 128 : (size_t)233472 / ctas - 1024 - 128; }
+
+// balanced split of the unit list into n_chunks contiguous runs by estimated cost (a run may only end after the last word of a
+// blob) -> chunk descriptors; returns false when fewer runs are possible
+static bool ko_split(const std::vector<KoUnit>& units, int n_chunks, KoChunks& out, size_t& max_bytes, uint32_t& max_words) {
+    const int n = (int)units.size();
+    uint64_t total = 0, run = 0;
+    for (const auto& u : units) total += u.cost;
+    std::vector<int> lo(1, 0);
+    for (int i = 0; i < n; ++i) {
+        const int c = (int)lo.size() - 1;
+        if (c + 1 < n_chunks && i > lo[(size_t)c] && units[(size_t)i - 1].last && run * n_chunks >= total * (uint64_t)(c + 1)) lo.push_back(i);
+        run += units[(size_t)i].cost;
+    }
+    if ((int)lo.size() != n_chunks) return false;
+    lo.push_back(n);
+    max_bytes = 0; max_words = 0;
+    std::vector<uint32_t> off((size_t)n + 1, 0);
+    for (int i = 0; i < n; ++i) off[(size_t)i + 1] = off[(size_t)i] + units[(size_t)i].bytes;
+    std::memset(&out, 0, sizeof(out));
+    for (int k = 0; k < n_chunks; ++k) {
+        KoChunk& c = out.c[k];
+        const int a = lo[(size_t)k], b = lo[(size_t)k + 1];
+        c.off = off[(size_t)a]; c.bytes = off[(size_t)b] - off[(size_t)a]; c.r0 = (uint32_t)a; c.n_words = (uint32_t)(b - a);
+        c.off_b = c.off_c = c.bytes;
+        for (int i = a; i < b; ++i) {
+            const KoUnit& u = units[(size_t)i];
+            if (u.kind == kSecA) ++c.n_a;
+            else if (u.kind == kSecB) { if (!c.n_b) c.off_b = off[(size_t)i] - c.off; ++c.n_b; }
+            else { if (!c.n_c) c.off_c = off[(size_t)i] - c.off; ++c.n_c; }
+        }
+        max_bytes = std::max<size_t>(max_bytes, c.bytes); max_words = std::max(max_words, c.n_words);
+    }
+    return true;
+}
+
+// Launch plan of the key-order kernel for this table (cached: it depends only on the key space and the table): the largest CTA
+// shape whose grid — tasks (32 keys each) x table chunks — fills the machine to >= 85 %, every chunk resident in shared memory.
+static void ko_plan(naqs_table_t* t, int sm_count) {
+    KoPlan best;
+    best.valid = -1;
+    double best_eff = -1.0;
+    const int64_t n_tasks = (1ll << t->n_qubits) / 32;
+    for (int s = 0; s < 3 && t->d_ko_stream; ++s) {
+        const int warps = kKoThreads[s] / 32;
+        const int64_t cta_slots = (int64_t)sm_count * kKoCtasPerSm[s];
+        const size_t cap = ko_smem_cap(kKoCtasPerSm[s]);
+        for (int ch = 1; ch <= kMaxChunks; ++ch) {
+            KoPlan p;
+            size_t max_bytes; uint32_t max_words;
+            if (!ko_split(t->ko_units, ch, p.chunks, max_bytes, max_words)) continue;
+            const uint32_t tw_stride = (max_words + 31) / 32 * 32;
+            const size_t tw_offset = (max_bytes + 127) & ~(size_t)127, smem = tw_offset + (size_t)warps * tw_stride * 4;
+            if (smem > cap) continue;
+            const int64_t ctas_full = (n_tasks + warps - 1) / warps;   // CTAs per chunk when every task has its own warp
+            int64_t gx;
+            double eff;
+            if (ctas_full * ch <= cta_slots) {
+                gx = ctas_full;
+                eff = (double)(n_tasks * ch) / (double)(cta_slots * warps);
+            } else {
+                gx = std::max<int64_t>(1, cta_slots / ch);
+                const int64_t waves = (n_tasks + gx * warps - 1) / (gx * warps);
+                eff = (double)n_tasks / (double)(waves * gx * warps) * (double)(gx * ch) / (double)cta_slots;
+            }
+            eff -= 0.005 * ch;
+            if (eff > best_eff + 1e-9) {
+                best_eff = eff;
+                best = p;
+                best.valid = 1; best.shape = s; best.n_chunks = ch; best.grid_x = (int)gx;
+                best.smem = (uint32_t)smem; best.tw_offset = (uint32_t)tw_offset; best.tw_stride = tw_stride;
+            }
+        }
+        if (best_eff >= 0.85) break;
+    }
+    t->ko_plan = best;
+}
+
+template <int SHAPE>
+static int launch_keyorder_shape(naqs_table_t* t, const KoPlan& p, const float2* dense32, const uint32_t* need, int64_t n_tasks, int64_t n_keys,
+                                 double2* partial, cudaStream_t stream) {
+    auto kern = eloc_keyorder_kernel<kKoThreads[SHAPE], kKoCtasPerSm[SHAPE]>;
+    static bool attr_set[64] = {false};  // per device: the attribute sticks to the function
+    if (!attr_set[t->device & 63]) {
+        NAQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ko_smem_cap(kKoCtasPerSm[SHAPE])));
+        attr_set[t->device & 63] = true;
+    }
+    KoView kv{t->d_ko_stream, t->d_ko_ht, t->ko_n_hi, t->ko_r_total_pad};
+    kern<<<dim3((unsigned)p.grid_x, (unsigned)p.n_chunks), kKoThreads[SHAPE], p.smem, stream>>>(kv, p.chunks, p.tw_offset, p.tw_stride, dense32, need,
+                                                                                                 n_tasks, n_keys, partial);
+    NAQS_LAUNCHED();
+    return NAQS_OK;
+}
+
+// key-order walk with the complex64 direct-address table: mark the row keys, run the kernel over all 2^N keys, finalise the rows
+static int launch_keyorder(naqs_table_t* t, const uint64_t* d_states, const void* d_psi, int psi_dtype, int64_t M_rows, double* d_eloc,
+                           cudaStream_t stream) {
+    const KoPlan& p = t->ko_plan;
+    const int64_t n_keys = 1ll << t->n_qubits, n_tasks = n_keys / 32;
+    const size_t bitmap_bytes = ((size_t)n_tasks * 4 + 255) & ~(size_t)255;
+    const size_t need_bytes = (size_t)p.n_chunks * n_keys * sizeof(double2) + bitmap_bytes;
+    if (t->partial_bytes < need_bytes) {
+        cudaFree(t->d_partial); t->d_partial = nullptr; t->partial_bytes = 0;
+        NAQS_CUDA(cudaMalloc((void**)&t->d_partial, need_bytes));
+        t->partial_bytes = need_bytes;
+    }
+    uint32_t* need_bits = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(t->d_partial) + (size_t)p.n_chunks * n_keys * sizeof(double2));
+    NAQS_CUDA(cudaMemsetAsync(need_bits, 0, bitmap_bytes, stream));
+    mark_keys_kernel<<<(unsigned)((M_rows + 255) / 256), 256, 0, stream>>>(d_states, M_rows, need_bits);
+    NAQS_LAUNCHED();
+    const float2* dense32 = t->d_dense32_ext ? t->d_dense32_ext : t->d_dense32;
+    int rc;
+    switch (p.shape) {
+        case 0: rc = launch_keyorder_shape<0>(t, p, dense32, need_bits, n_tasks, n_keys, t->d_partial, stream); break;
+        case 1: rc = launch_keyorder_shape<1>(t, p, dense32, need_bits, n_tasks, n_keys, t->d_partial, stream); break;
+        default: rc = launch_keyorder_shape<2>(t, p, dense32, need_bits, n_tasks, n_keys, t->d_partial, stream); break;
+    }
+    if (rc) return rc;
+    eloc_rows_finalize_kernel<<<(unsigned)((M_rows + 255) / 256), 256, 0, stream>>>(t->d_partial, p.n_chunks, n_keys, d_states, d_psi, psi_dtype,
+                                                                                  M_rows, reinterpret_cast<double2*>(d_eloc));
+    NAQS_LAUNCHED();
+    return NAQS_OK;
+}
+
 template <int NW, int NN>
 static int launch_sliced(naqs_table_t* t, const uint64_t* d_states, const void* d_psi, int psi_dtype, int64_t M, double* d_eloc,
                          cudaStream_t stream) {
@@ -576,7 +730,7 @@ static int launch_sliced(naqs_table_t* t, const uint64_t* d_states, const void* 
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, t->device);
     // key-order mode: dense (direct-address) lookup and a batch that covers at least 1/8 of the key space
     const bool keyorder = NW == 1 && t->lookup_kind == NAQS_LOOKUP_DENSE && t->n_qubits <= 26 &&
-                          (t->dense32_valid || (M >= (1ll << t->n_qubits) / 8 && !getenv("NAQS_ELOC_NO_KEYORDER")));
+                          (t->dense32_valid || (M >= (1ll << t->n_qubits) / 8 && !t->env_no_keyorder));
     const int64_t M_rows = M;
     if (keyorder) M = 1ll << t->n_qubits;  // launch shape is chosen for the number of threads that actually run
     // pick the launch shape: large CTAs when there are at least two waves of them, else smaller CTAs, and split the
@@ -605,6 +759,11 @@ static int launch_sliced(naqs_table_t* t, const uint64_t* d_states, const void* 
     const bool hash = t->lookup_kind == NAQS_LOOKUP_HASH;
     const bool secf = t->sector.enabled != 0 && t->dense32_valid && t->d_dense32_ext != nullptr;
     if constexpr (NW == 1) {
+        // complex64 table, no sector test needed in the kernel: the dedicated key-order kernel (keyorder.cuh)
+        if (keyorder && t->dense32_valid && !secf && t->n_qubits >= 5 && t->d_ko_stream && !t->ko_disabled) {
+            if (t->ko_plan.valid == 0) ko_plan(t, sm_count);
+            if (t->ko_plan.valid == 1) return launch_keyorder(t, d_states, d_psi, psi_dtype, M_rows, d_eloc, stream);
+        }
         if (keyorder) {
 #define NAQS_KO(CFG, SEC, P32) launch_sliced_cfg<NW, NN, CFG, kLookDense, SEC, true, P32>(t, d_states, d_psi, psi_dtype, M_rows, d_eloc, stream, n_chunks, sm_count)
             switch (cfg * 4 + (secf ? 2 : 0) + (t->dense32_valid ? 1 : 0)) {

@@ -31,14 +31,15 @@ def _world(group):
 
 
 def gather_table(keys, psi, group=None, equal_sizes=False, out=None):
-    """All-gather the (key, psi) shards of every rank -> (keys [T, W] int64 bit patterns, psi [T] complex).
+    """All-gather the (key, psi) shards of every rank -> (keys [T, W] int64 bit patterns, psi [T] complex, T).
 
     equal_sizes=True skips the size exchange (and its host synchronisation) when every rank is known to hold the same
     number of rows; out=(g_keys, g_psi) reuses preallocated gather buffers.
 
-    Shards may have different lengths: each is padded to the longest with (its own first key or 0, psi = 0); a padded
-    entry adds exactly 0 to the amplitude of a key (duplicates are summed by the lookup build), so no un-padding pass
-    is needed on the device.  Returns the padded gathered arrays and the true total count."""
+    Shards may have different lengths: each is padded to the longest for the collective and the padding is REMOVED again
+    (by the exchanged counts) before anything is returned — a padded entry must never reach a lookup build: with
+    duplicates_equal / assume_unique the build keeps ONE copy of a key with a plain store, so a padded (key, 0) pair could
+    replace the real amplitude of that key."""
     world, rank = _world(group)
     keys = keys if keys.dim() == 2 else keys.reshape(-1, 1)
     if world == 1:
@@ -53,8 +54,7 @@ def gather_table(keys, psi, group=None, equal_sizes=False, out=None):
     n_max = max(counts)
     if keys.shape[0] < n_max:
         pad = n_max - keys.shape[0]
-        fill = keys[:1] if keys.shape[0] > 0 else torch.zeros((1, keys.shape[1]), dtype=keys.dtype, device=keys.device)
-        keys = torch.cat([keys, fill.expand(pad, -1)], 0)
+        keys = torch.cat([keys, torch.zeros((pad, keys.shape[1]), dtype=keys.dtype, device=keys.device)], 0)
         psi = torch.cat([psi, torch.zeros(pad, dtype=psi.dtype, device=psi.device)], 0)
     if out is not None:
         g_keys, g_psi = out
@@ -67,7 +67,11 @@ def gather_table(keys, psi, group=None, equal_sizes=False, out=None):
     else:  # gloo: list form
         dist.all_gather(list(g_keys.chunk(world, 0)), keys.contiguous(), group=group)
         dist.all_gather(list(torch.view_as_real(g_psi).chunk(world, 0)), torch.view_as_real(psi.contiguous()), group=group)
-    return g_keys, g_psi, sum(counts)
+    total = sum(counts)
+    if total != world * n_max:  # uneven shards: drop the padding rows (block r keeps its first counts[r] rows)
+        keep = (torch.arange(n_max, device=keys.device)[None, :] < torch.tensor(counts, device=keys.device)[:, None]).reshape(-1)
+        g_keys, g_psi = g_keys[keep], g_psi[keep]
+    return g_keys, g_psi, total
 
 
 INT32_MIN = -(2 ** 31)  # bit pattern of -0.0f: "absent" for the MAX all-reduce and a numeric zero for the kernel

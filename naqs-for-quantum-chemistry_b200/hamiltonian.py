@@ -49,6 +49,10 @@ class PauliHamiltonian:
 
 
 class PauliHamiltonianB200:
+    # defaults for objects assembled without __init__ (tests drive the mirror from a packed table)
+    track_seen = True
+    _seen_chunks, _seen_count = (), 0
+
     def __init__(self, hilbert, qubit_hamiltonian, restricted_idxs=None, n_excitations_max=None, verbose=False,
                  dtype=np.float32, device=None):
         self.hilbert = hilbert
@@ -84,6 +88,11 @@ class PauliHamiltonianB200:
         self._cached_idxs = np.array([], dtype=idt)
         self._frozen_H = False
         self._restricted_H = None
+        # states that went through the fused (stateless) local_energy path but are not in the CSR cache: the reference's
+        # update_H would have cached their rows as a side effect (energy.py:245), and its solve_H / save rely on that
+        # (energy.py:559,777,447).  Their rows are computed on demand by get_H(idxs) / save(); see _materialize_seen.
+        self.track_seen = True
+        self._seen_chunks, self._seen_count = [], 0
         if verbose:
             print(f"Pauli Hamiltonian has K={self.table.K} terms, {self.table.Kxy} unique XY masks, {self.table.Kyz} unique YZ masks "
                   f"(device {self.table.device}).")
@@ -94,6 +103,8 @@ class PauliHamiltonianB200:
         (energy.py:247-248).  Stateless: nothing is cached.  assume_unique=True as in the reference's call
         update_H(states_idx, check_unseen=True, assume_unique=True) (energy.py:245)."""
         on_device = (torch.is_tensor(states_idx) and states_idx.is_cuda) or (torch.is_tensor(psi) and psi.is_cuda)
+        if self.track_seen and not self._frozen_H and not on_device:
+            self._note_seen(states_idx)
         if ret_numpy and not on_device:
             # host-resident batch (the reference's situation: sampler output is moved to the CPU, nade.py:727-733):
             # one C-ABI call that uploads, computes and downloads (naqs_eloc_host)
@@ -135,6 +146,22 @@ class PauliHamiltonianB200:
         return eigsh(self.linear_operator(states_idx), k=k, which="SA", tol=tol)
 
     # ------------------------------------------------------------------ reference API
+    def _note_seen(self, states_idx):
+        a = self.hilbert.to_idx_array(states_idx).reshape(-1)
+        self._seen_chunks = list(self._seen_chunks) + [a.copy()]
+        self._seen_count += len(a)
+        if len(self._seen_chunks) > 64 or self._seen_count > 4 * max(len(self._cached_idxs), 1 << 16):
+            u = np.unique(np.concatenate(self._seen_chunks))
+            self._seen_chunks, self._seen_count = [u], len(u)
+
+    def _materialize_seen(self):
+        """Rows of every state that went through the fused path since the last call -> CSR cache (what the reference's
+        update_H side effect at energy.py:245 would have produced)."""
+        if self._seen_chunks and not self._frozen_H:
+            seen = np.unique(np.concatenate(self._seen_chunks))
+            self._seen_chunks, self._seen_count = [], 0
+            self.update_H(seen, check_unseen=True, assume_unique=True)
+
     def _rows_csr(self, state_i_idx):
         indptr, cols, ridx, vals = self.table.rows(state_i_idx.astype(np.int64), with_restricted_index=True)
         indptr, ridx, vals = indptr.cpu().numpy(), ridx.cpu().numpy(), vals.cpu().numpy()
@@ -163,8 +190,14 @@ class PauliHamiltonianB200:
         """hamiltonian.py:96-111.  (The reference's full-sector shortcut returns rows in restricted order even
         when `idxs` is permuted — quirk q1 of SURVEY.md §8a; here the caller's order is always kept.)"""
         if idxs is not None:
-            idxs = self.hilbert.full2restricted_idx(idxs.detach().cpu().numpy() if torch.is_tensor(idxs) else idxs)
-            return self.__get_new_H_subspace(idxs)
+            idxs = idxs.detach().cpu().numpy() if torch.is_tensor(idxs) else np.asarray(idxs)
+            if not self._frozen_H:
+                # the fused local_energy path caches nothing, so the rows the reference would find in its cache (filled by
+                # the update_H of calculate_local_energy, energy.py:245) are computed here on demand — solve_H
+                # (energy.py:559,777) calls get_H without update_H
+                self.update_H(idxs.reshape(-1), check_unseen=True)
+            return self.__get_new_H_subspace(self.hilbert.full2restricted_idx(idxs))
+        self._materialize_seen()
         return self.H
 
     def get_restricted_H(self):
@@ -226,6 +259,7 @@ class PauliHamiltonianB200:
         self.load_H(fname_H)
 
     def save(self, fname, fname_H=None):
+        self._materialize_seen()  # the reference saves the rows of every state seen so far (energy.py:447)
         fname, fname_H = PauliHamiltonian._format_fnames(fname, fname_H)
         d = os.path.dirname(fname)
         if d:

@@ -86,6 +86,24 @@ def test_pack_terms_product_matches_reference_table(mol):
     assert np.array_equal(pxy[:, 0], xy) and np.array_equal(pyz[:, 0], yz) and np.array_equal(pc, c)
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/molecules"), reason="needs the reference's pickles (build container only)")
+@pytest.mark.parametrize("mol", ["H2O", "N2", "N2_1.5", "H2S", "NH3", "C2", "Li2O"])
+def test_pkl_loader_and_pack_terms_reproduce_reference_tables_bitwise(mol):
+    """load_qubit_hamiltonian (openfermion-free unpickler) + pack_terms against the tables the reference's own
+    __calc_coupling_info produced (tests/golden/make_golden.py), bit patterns included: H2O / N2_1.5 / H2S carry odd-nY
+    terms whose coefficients are signed zeros (hamiltonian.py:416,424)."""
+    xy, yz, c, N, na, nb = load_table(mol)
+    op = naqs_b200.load_qubit_hamiltonian(f"/root/reference/molecules/{mol}/{mol}_qubit_hamiltonian.pkl")
+    assert op.many_body_order() <= N
+    pxy, pyz, pc = naqs_b200.pack_terms(op.terms, N)
+    assert pxy.shape == (len(c), 1)
+    assert np.array_equal(pxy[:, 0], xy) and np.array_equal(pyz[:, 0], yz)
+    assert np.array_equal(pc.view(np.uint64), c.view(np.uint64))  # bitwise: -0.0 != +0.0 here
+    if mol in ("H2O", "N2_1.5", "H2S"):
+        n_y = np.array([bin(int(a) & int(b)).count("1") for a, b in zip(pxy[:, 0], pyz[:, 0])])
+        assert (n_y % 2 == 1).any() and np.all(pc[n_y % 2 == 1] == 0.0)
+
+
 def test_pack_terms_filters_and_odd_y():
     terms = {(): 1.5 + 0j, ((0, "X"), (1, "Y")): 2.0 + 0j, ((0, "Y"), (3, "Y")): 0.25 + 0j, ((2, "Z"),): -1.0 + 0j,
              ((1, "X"), (2, "X"), (3, "X"), (4, "X")): 0.5 + 1e-9j}

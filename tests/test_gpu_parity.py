@@ -572,6 +572,17 @@ def _mgpu_worker(rank, world, port, q):
         assert nd.can_allreduce_table(t, torch.from_numpy(psi))
         diff = float((eloc2 - eloc).abs().max() / eloc.abs().max())
         assert diff < 1e-13, diff
+        # uneven shards through the all-GATHER exchange with keep-one builds (a padded (key, 0) pair must never
+        # replace a real amplitude): hash lookup with complex64 psi, and complex128 psi (which cannot take the all-reduced table)
+        table_h = naqs_b200.DeviceTermTable(xy, yz, c, N, na, nb, device=f"cuda:{rank}")
+        g_k, g_p, total = nd.gather_table(table_h._keys(st[lo:hi]), torch.from_numpy(psi[lo:hi]).to(table_h.device))
+        assert total == len(st) and g_k.shape[0] == len(st)
+        table_h.build_lookup(g_k, g_p, kind=naqs_b200.table.LOOKUP_HASH, duplicates_equal=True)
+        eloc3 = table_h.local_energy(st[lo:hi], psi[lo:hi], rebuild_lookup=False)
+        eloc4, _ = nd.sharded_local_energy(t, st[lo:hi], psi[lo:hi].astype(np.complex128), duplicates_equal=True)
+        for other in (eloc3, eloc4):
+            diff = float((other - eloc).abs().max() / eloc.abs().max())
+            assert diff < 1e-13, diff
         q.put((rank, lo, hi, naqs_b200._lib.complex_from_pairs(eloc), stats))
         dist.barrier()
     finally:
