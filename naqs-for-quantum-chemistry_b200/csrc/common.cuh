@@ -142,11 +142,12 @@ struct LookupView {
     const HashBucket* buckets;  // [n_buckets] (kind HASH, keys <= 63 bits)
     unsigned bmask;          // n_buckets - 1
     int bshift;              // 32 - log2(n_buckets)
-    const uint32_t* filter;  // blocked Bloom filter over the table keys (2^(32 - filter_wshift) words) or nullptr
+    const uint32_t* filter;  // blocked Bloom filter over the table keys (filter_mask / 4 + 1 words) or nullptr
     const float2* dense32;   // [2^N] complex64 copy of the dense table (unique keys + complex64 psi only) or nullptr
-    int filter_wshift;       // filter word = hash32 >> filter_wshift
-    const uint32_t* filter_small;  // 2^14-word companion of a larger filter (same hashes, its own word index) or nullptr
+    uint32_t filter_mask;    // byte offset of a key's filter word = lin-hash word & filter_mask (= 4 * n_words - 4)
+    const uint32_t* filter_small;  // 2^14-word companion of a larger filter (same hashes, the low 14 word bits) or nullptr
     int filter_in_smem;      // the launch copies the filter into shared memory (it has 2^14 words and the shape has room)
+    int* flags;              // bit 0: a key outside [0, 2^n_qubits) was seen (naqs_table_check reports and clears it)
 };
 
 
@@ -162,27 +163,56 @@ __host__ __device__ inline uint32_t hash32(unsigned long long k0, unsigned long 
     return (uint32_t)k0 * 0x9E3779B1u + (uint32_t)(k0 >> 32) * 0x85EBCA6Bu + (uint32_t)k1 * 0xC2B2AE35u +
            (uint32_t)(k1 >> 32) * 0x27D4EB2Fu;
 }
-__host__ __device__ inline uint32_t hash32b(unsigned long long k0) {
-    return (uint32_t)k0 * 0x7FEB352Du + (uint32_t)(k0 >> 32) * 0x846CA68Bu;
-}
 __host__ __device__ inline unsigned long long hash_slot(unsigned long long k0, unsigned long long k1, int shift) {
     return (unsigned long long)(hash32(k0, k1) >> shift);
 }
 
 // Bloom filter of the hash lookups.  In a sparse VMC batch almost every coupled state is NOT in the table; the filter
 // answers those without the global sector read of a bucket / slot.  Blocked: both bits of a key live in ONE 32-bit word
-// (one load per test) — the word from the top bits of the table hash, the two bit positions from the top bits of a
-// second product.  2^14 words (64 KB, >= 4 bits per key) up to 2^17 keys — that size is copied into shared memory by
+// (one load per test).  2^14 words (64 KB, >= 4 bits per key) up to 2^17 keys — that size is copied into shared memory by
 // every CTA of the 1024-thread launch shape and consulted for every (state, group) pair; larger batches get >= 16 bits
 // per key, up to 2^22 words (16 MB, L2-resident), consulted from global memory before a bucket / slot probe.
+//
+// The hashes are GF(2)-LINEAR in the key (XOR of one pseudo-random 64-bit column per set key bit): hash(s ^ u) =
+// hash(s) ^ hash(u), so the fused kernel keeps hash(s) per thread, reads hash(u) with the group's flip mask (warp-uniform)
+// and pays two XORs per coupled state instead of two multiplies and shifts.  A random linear map is a universal hash
+// family: the false-positive rate is that of an ideal hash in expectation.  Second benefit: the shared-memory BANK of the
+// filter word is bits 2..6 of the word hash, so bank(s ^ u) = bank(s) ^ bank(u) — a warp whose 32 states have pairwise
+// different bank(s) probes 32 different banks for EVERY group (bin_states_kernel arranges the batch that way).
+//   hw: byte offset of the filter word (bits 0-1 clear; a filter of 2^L words uses hw & (4 * 2^L - 4))
+//   hb: low 5 bits = position b of the key's first bit; the second bit sits 13 positions further (mod 32):
+//       set  word |= rotl(0x2001, b),   test  (~rotr(word, b) & 0x2001) == 0
 constexpr int kFilterLog2WordsSmem = 14, kFilterLog2WordsMax = 22;
 constexpr uint32_t kFilterBytes = (1u << kFilterLog2WordsSmem) * 4;  // the shared-memory copy
-__host__ __device__ inline void filter_word_bits(unsigned long long k0, unsigned long long k1, uint32_t h, int wshift,
-                                                 uint32_t& word, uint32_t& b1, uint32_t& b2) {
-    const uint32_t hb = hash32b(k0) + (uint32_t)k1 * 0x165667B1u + (uint32_t)(k1 >> 32) * 0xD3A2646Cu;
-    word = h >> wshift;
-    b1 = hb >> 27;
-    b2 = (hb >> 22) & 31u;
+constexpr uint32_t kFilterPattern = 0x2001u;
+__host__ __device__ inline void lin_hash_word(uint32_t x, int word_index, uint32_t& hw, uint32_t& hb) {
+    while (x) {
+#ifdef __CUDA_ARCH__
+        const int i = __ffs((int)x) - 1;
+#else
+        const int i = __builtin_ctz(x);
+#endif
+        x &= x - 1;
+        const unsigned long long m = mix64(0x9E3779B97F4A7C15ull * (unsigned long long)(word_index * 32 + i + 1));
+        hw ^= (uint32_t)m & ~3u;
+        hb ^= (uint32_t)(m >> 32);
+    }
+}
+__host__ __device__ inline void lin_hash_key64(const uint64_t* key, int words, uint32_t& hw, uint32_t& hb) {
+    hw = 0; hb = 0;
+    for (int w = 0; w < words; ++w) {
+        lin_hash_word((uint32_t)key[w], 2 * w, hw, hb);
+        lin_hash_word((uint32_t)(key[w] >> 32), 2 * w + 1, hw, hb);
+    }
+}
+__host__ __device__ inline uint32_t filter_insert_bits(uint32_t hb) {
+    const uint32_t b = hb & 31u;
+    return (kFilterPattern << b) | (kFilterPattern >> ((32u - b) & 31u));
+}
+__host__ __device__ inline bool filter_test_word(uint32_t word, uint32_t hb) {
+    const uint32_t b = hb & 31u;
+    const uint32_t r = (word >> b) | (word << ((32u - b) & 31u));
+    return (~r & kFilterPattern) == 0u;
 }
 
 }  // namespace naqs
@@ -246,6 +276,10 @@ struct naqs_table {
     void* h_pinned = nullptr;
     size_t pinned_bytes = 0;
     cudaStream_t own_stream = nullptr;
+    int* d_flags = nullptr;   // [4] device flags (bit 0 of [0]: key out of range), see naqs_table_check
+    int32_t* d_perm = nullptr;      // bank-binned order of a hash-lookup batch (bin_states_kernel) + 33 counters in front
+    size_t perm_bytes = 0;
+    bool env_no_bin = false;
 
     naqs::TableView view() const { return naqs::TableView{d_yz, d_coeff, d_gxy, d_gstart, (int)K, (int)G, f32}; }
     naqs::LookupView lookup() const {
@@ -257,7 +291,7 @@ struct naqs_table {
                                 d_buckets, (unsigned)(n_buckets > 0 ? n_buckets - 1 : 0), bshift,
                                 filter_valid ? d_filter + (filter_small_valid ? (1u << naqs::kFilterLog2WordsSmem) : 0u) : nullptr,
                                 dense32_valid ? (d_dense32_ext ? d_dense32_ext : d_dense32) : nullptr,
-                                32 - filter_log2w, filter_valid && filter_small_valid ? d_filter : nullptr, 0};
+                                (uint32_t)((4u << filter_log2w) - 4u), filter_valid && filter_small_valid ? d_filter : nullptr, 0, d_flags};
     }
 };
 

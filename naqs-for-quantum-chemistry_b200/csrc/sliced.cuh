@@ -17,10 +17,12 @@
 // fully serial order and is bit-exact for every group.
 //
 // Stream layout (device memory, staged into shared memory tile by tile with cp.async.bulk + mbarrier):
-//   A record (8 groups x 4 bits):  T[NN][16] u32 | U[8][NW] u32 (+ U << 3 when NW == 1) | LUT[8][16] f64
-//   B record (5 groups x 6 bits):  T[NN][16] u32 | U[8][NW] u32 (+ U << 3 when NW == 1) | LUT[5][64] f64
+//   A record (8 groups x 4 bits):  T[NN][16] u32 | U[8][NW] u32 (+ U << 3 when NW == 1) | HW[8] HB[8] u32 | LUT[8][16] f64
+//   B record (5 groups x 6 bits):  T[NN][16] u32 | U[8][NW] u32 (+ U << 3 when NW == 1) | HW[8] HB[8] u32 | LUT[5][64] f64
 //   C blob   (<= 150 terms of one big group; a longer group is several blobs with the same u, each contributing
-//             H_blob * psi(s ^ u) on its own):  header{n_words, -, -, -, u[4]} | n_words x ( T[NN][16] u32 | LUT[5][64] f64 )
+//             H_blob * psi(s ^ u) on its own):  header{n_words, HW, HB, -, u[4]} | n_words x ( T[NN][16] u32 | LUT[5][64] f64 )
+//   HW / HB: the GF(2)-linear Bloom-filter hashes of the flip mask u (lin_hash, common.cuh).  Linear means
+//   hash(s ^ u) = hash(s) ^ hash(u): the filter test of a coupled state costs two XORs with the per-thread hash(s).
 #pragma once
 #include <algorithm>
 #include <cstring>
@@ -58,7 +60,7 @@ struct HostGroup {
 inline int nibbles_for(int n_qubits) { return n_qubits <= 20 ? 5 : (n_qubits <= 32 ? 8 : (n_qubits <= 63 ? 16 : 32)); }
 // flip masks of a record: 8 slots of nw words; single-word keys carry a second copy shifted left by 3 (= byte offsets into
 // the complex64 direct-address table, whose base is aligned to its size: entry address = (base ^ key * 8) ^ (u * 8))
-inline size_t u_bytes(int nw) { return nw == 1 ? 64 : (size_t)32 * nw; }
+inline size_t u_bytes(int nw) { return (nw == 1 ? 64 : (size_t)32 * nw) + 64; }  // masks + their filter hashes HW[8], HB[8]
 inline size_t rec_bytes_A(int nn, int nw) { return (size_t)64 * nn + u_bytes(nw) + 8 * 16 * 8; }
 inline size_t rec_bytes_B(int nn, int nw) { return (size_t)64 * nn + u_bytes(nw) + 5 * 64 * 8; }
 inline size_t rec_bytes_C(int nn) { return (size_t)64 * nn + 5 * 64 * 8; }  // one word of a big group: 5 chunks of <= 6 terms
@@ -126,6 +128,12 @@ inline void build_sliced_host(const std::vector<HostGroup>& groups, int n_qubits
                 for (int t = 0; t < n; ++t) yz_of_bit[j * bits + t] = g->yz.data() + (size_t)t * nw;
                 for (int w = 0; w < nw; ++w) U[j * nw + w] = g ? g->u[w] : 0u;
                 if (nw == 1) U[8 + j] = g ? g->u[0] << 3 : 0u;
+                {
+                    uint32_t* HWB = reinterpret_cast<uint32_t*>(p + 64 * nn + u_bytes(nw) - 64);
+                    uint32_t hw = 0, hb = 0;
+                    if (g) for (int w = 0; w < nw; ++w) lin_hash_word(g->u[w], w, hw, hb);
+                    HWB[j] = hw; HWB[8 + j] = hb;
+                }
                 for (unsigned pat = 0; pat < (1u << bits); ++pat) L[j * (1 << bits) + pat] = g ? lut_entry(g->c.data(), n, pat) : 0.0;
             }
             fill_nibble_tables(p, nn, nw, yz_of_bit, per * bits);
@@ -150,7 +158,8 @@ inline void build_sliced_host(const std::vector<HostGroup>& groups, int n_qubits
             S.resize(off + kBlobHeader + nwords * rc, 0);
             uint32_t* hdr = reinterpret_cast<uint32_t*>(S.data() + off);
             hdr[0] = (uint32_t)nwords;
-            for (int w = 0; w < nw; ++w) hdr[4 + w] = g->u[w];
+            hdr[1] = hdr[2] = 0;
+            for (int w = 0; w < nw; ++w) { hdr[4 + w] = g->u[w]; lin_hash_word(g->u[w], w, hdr[1], hdr[2]); }
             for (size_t q = 0; q < nwords; ++q) {
                 unsigned char* p = S.data() + off + kBlobHeader + q * rc;
                 const uint32_t* yz_of_bit[32] = {nullptr};

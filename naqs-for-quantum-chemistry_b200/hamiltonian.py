@@ -20,6 +20,13 @@ from .hilbert import Encoding
 from .pauli import pack_terms
 from .table import DeviceTermTable
 
+# Quirk q1 of SURVEY.md §8a: the reference's get_H returns get_restricted_H() — rows AND columns in restricted order —
+# whenever the batch has as many states as the sector (hamiltonian.py:100-105), whatever order the batch is in, so H and
+# psi are misaligned for a full sample (LiH: every VMC iteration samples all 225 sector states, in ascending key order).
+# Default: NOT reproduced (the caller's order is kept, E_loc is the physical one).  NAQS_ELOC_REFERENCE_QUIRKS=1 (or
+# install(reference_quirks=True)) reproduces it, for bitwise trajectory parity with the reference on such batches.
+REFERENCE_QUIRKS = os.environ.get("NAQS_ELOC_REFERENCE_QUIRKS", "0") not in ("", "0")
+
 
 class PauliHamiltonian:
 
@@ -59,6 +66,7 @@ class PauliHamiltonianB200:
         assert self.hilbert.encoding.name == Encoding.SIGNED.name, "PauliCouplings requires Encoding.SIGNED."
         self.qubit_hamiltonian = qubit_hamiltonian
         self.restricted_idxs = self.hilbert.full2restricted_idx(restricted_idxs)
+        self._restricted_full_idxs = None if restricted_idxs is None else self.hilbert.to_idx_array(restricted_idxs).reshape(-1)
         self.n_excitations_max = n_excitations_max
         self.dtype = dtype
         self.verbose = verbose
@@ -103,6 +111,9 @@ class PauliHamiltonianB200:
         (energy.py:247-248).  Stateless: nothing is cached.  assume_unique=True as in the reference's call
         update_H(states_idx, check_unseen=True, assume_unique=True) (energy.py:245)."""
         on_device = (torch.is_tensor(states_idx) and states_idx.is_cuda) or (torch.is_tensor(psi) and psi.is_cuda)
+        if REFERENCE_QUIRKS and self._is_full_sample(states_idx):
+            # q1: the reference pairs psi[j] with the j-th sector state in RESTRICTED order here (see REFERENCE_QUIRKS)
+            states_idx = self._restricted_full_idxs
         if self.track_seen and not self._frozen_H and not on_device:
             self._note_seen(states_idx)
         if ret_numpy and not on_device:
@@ -144,6 +155,13 @@ class PauliHamiltonianB200:
         scipy eigs on the cached CSR, energy.py:762-786) by Lanczos on the matrix-free operator."""
         from scipy.sparse.linalg import eigsh
         return eigsh(self.linear_operator(states_idx), k=k, which="SA", tol=tol)
+
+    def _is_full_sample(self, idxs):
+        r = getattr(self, "_restricted_full_idxs", None)
+        try:
+            return r is not None and len(idxs) == len(r)
+        except TypeError:
+            return False
 
     # ------------------------------------------------------------------ reference API
     def _note_seen(self, states_idx):
@@ -188,7 +206,7 @@ class PauliHamiltonianB200:
 
     def get_H(self, idxs=None):
         """hamiltonian.py:96-111.  (The reference's full-sector shortcut returns rows in restricted order even
-        when `idxs` is permuted — quirk q1 of SURVEY.md §8a; here the caller's order is always kept.)"""
+        when `idxs` is permuted — quirk q1 of SURVEY.md §8a; here the caller's order is kept unless REFERENCE_QUIRKS is set.)"""
         if idxs is not None:
             idxs = idxs.detach().cpu().numpy() if torch.is_tensor(idxs) else np.asarray(idxs)
             if not self._frozen_H:
@@ -196,6 +214,8 @@ class PauliHamiltonianB200:
                 # the update_H of calculate_local_energy, energy.py:245) are computed here on demand — solve_H
                 # (energy.py:559,777) calls get_H without update_H
                 self.update_H(idxs.reshape(-1), check_unseen=True)
+            if REFERENCE_QUIRKS and self._is_full_sample(idxs):
+                return self.get_restricted_H()  # hamiltonian.py:100-105 (q1)
             return self.__get_new_H_subspace(self.hilbert.full2restricted_idx(idxs))
         self._materialize_seen()
         return self.H

@@ -18,9 +18,13 @@ from . import hamiltonian as _hamiltonian
 from . import hamiltonian_math, hilbert_math, sparse_math
 
 
-def install(reference_root=None, patch_level0=True, patch_level1=True):
+def install(reference_root=None, patch_level0=True, patch_level1=True, reference_quirks=None):
+    """reference_quirks=True reproduces quirk q1 (hamiltonian.REFERENCE_QUIRKS) for bitwise parity with the reference on
+    full-sector batches; None keeps the NAQS_ELOC_REFERENCE_QUIRKS environment setting (default off)."""
     if os.environ.get("NAQS_ELOC_BACKEND", "b200") == "reference":
         return False
+    if reference_quirks is not None:
+        _hamiltonian.REFERENCE_QUIRKS = bool(reference_quirks)
     if reference_root and reference_root not in sys.path:
         sys.path.insert(0, reference_root)
     if patch_level0:

@@ -151,15 +151,17 @@ def _prepare(backend, root):
 
 
 def run_vmc(molecule="LiH", iters=20, seed=111, backend="b200", n_samps=int(1e5), n_hid=64, n_hid_phase=512, n_layer_phase=2,
-            n_unq_samps_min=int(1e4), n_unq_samps_max=int(1e5), final_solve=True, quiet=True):
+            n_unq_samps_min=int(1e4), n_unq_samps_max=int(1e5), final_solve=True, quiet=True, model_device=None, record_psi=False):
     """experiments/_base._run with the flags of experiments/bash/naqs/batch_train.sh:14 for `iters` iterations.
-    -> dict(idx=[per-iteration int64 arrays], eloc=[per-iteration float32 [M, 2]], log_eloc, log_var, times={...}, eig)."""
+    -> dict(idx=[per-iteration int64 arrays], eloc=[per-iteration float32 [M, 2]], log_eloc, log_var, times={...}, eig).
+    model_device: None = the reference's default (cuda when available, wavefunction.py:33-34); "cpu" makes the whole
+    trajectory bitwise reproducible, so two backends can be compared iteration by iteration."""
     import torch
     root = tree_root()
     if root is None:
         raise RuntimeError("no reference tree (neither /root/reference nor oracle/_ref/tree)")
     mods = _prepare(backend, root)
-    rec = {"idx": [], "eloc": [], "t_eloc": [], "t_sample": [], "t_state2idx": [], "t_step": [], "eig": None}
+    rec = {"idx": [], "eloc": [], "psi": [], "t_eloc": [], "t_sample": [], "t_state2idx": [], "t_step": [], "eig": None}
     OB = mods.energy.OptimizerBase
     inner = OB.calculate_local_energy
 
@@ -175,6 +177,8 @@ def run_vmc(molecule="LiH", iters=20, seed=111, backend="b200", n_samps=int(1e5)
         rec["t_eloc"].append(time.perf_counter() - t)
         rec["idx"].append(np.asarray(states_idx.detach().cpu().numpy() if torch.is_tensor(states_idx) else states_idx).astype(np.int64).reshape(-1))
         rec["eloc"].append(out.detach().cpu().numpy().copy() if torch.is_tensor(out) else np.asarray(out))
+        if record_psi and psi is not None:
+            rec["psi"].append(psi.detach().cpu().numpy().copy() if torch.is_tensor(psi) else np.asarray(psi))
         return out
 
     OB.calculate_local_energy = recording_eloc
@@ -190,6 +194,12 @@ def run_vmc(molecule="LiH", iters=20, seed=111, backend="b200", n_samps=int(1e5)
 
     OB._SGD_step = timed_step
     wf_mod = importlib.import_module("src.naqs.wavefunction")
+    if model_device is not None:
+        base_init = wf_mod._NAQSComplex_Base.__init__
+
+        def init_on(self, *a, device=None, **k):
+            return base_init(self, *a, device=model_device, **k)
+        wf_mod._NAQSComplex_Base.__init__ = init_on
     hil_mod = importlib.import_module("src.utils.hilbert")
 
     def timed(cls, name, key):
@@ -250,6 +260,7 @@ def run_vmc(molecule="LiH", iters=20, seed=111, backend="b200", n_samps=int(1e5)
 def save_record(rec, path):
     arrays = {f"idx_{i}": a for i, a in enumerate(rec["idx"])}
     arrays.update({f"eloc_{i}": a for i, a in enumerate(rec["eloc"])})
+    arrays.update({f"psi_{i}": a for i, a in enumerate(rec.get("psi", []))})
     meta = {k: rec[k] for k in ("t_eloc", "t_sample", "t_state2idx", "t_step", "eig", "log_eloc", "log_var", "backend")}
     np.savez(path, meta=np.array(json.dumps(meta)), n=np.array(len(rec["idx"])), **arrays)
 
@@ -260,6 +271,7 @@ def load_record(path):
     n = int(z["n"])
     rec["idx"] = [z[f"idx_{i}"] for i in range(n)]
     rec["eloc"] = [z[f"eloc_{i}"] for i in range(n)]
+    rec["psi"] = [z[f"psi_{i}"] for i in range(n) if f"psi_{i}" in z.files]
     return rec
 
 
@@ -274,10 +286,12 @@ def main():
     ap.add_argument("--n-unq-max", type=int, default=int(1e5))
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--model-device", default=None)
+    ap.add_argument("--record-psi", action="store_true")
     ap.add_argument("--out", required=True)
     a = ap.parse_args()
     rec = run_vmc(a.molecule, a.iters, a.seed, a.backend, n_samps=a.n_samps, n_unq_samps_min=a.n_unq_min, n_unq_samps_max=a.n_unq_max,
-                  final_solve=not a.no_solve, quiet=not a.verbose)
+                  final_solve=not a.no_solve, quiet=not a.verbose, model_device=a.model_device, record_psi=a.record_psi)
     save_record(rec, a.out)
     print(json.dumps({"backend": a.backend, "iters": len(rec["log_eloc"]), "eloc_calls": len(rec["eloc"]), "last_E": rec["log_eloc"][-1] if rec["log_eloc"] else None,
                       "eig": rec["eig"], "ms_step": 1e3 * float(np.mean(rec["t_step"])) if rec["t_step"] else None,
