@@ -218,6 +218,49 @@ def pipe_peaks():
 
 
 # ----------------------------------------------------------------------------------------- reference arm
+# ---------------------------------------------------------------------------------------------- pipe roofline (live)
+# Algorithmic work of the two fused formulations per WARP UNIT (32 states x one record of the term stream), DESIGN.md §6:
+# (warp instructions, L1TEX wavefronts).  The counts are those of the formulation, not of the compiled loop — loop
+# control, address arithmetic beyond one LOP3 / IADD per access, queue traffic of the hash walk's survivors and bank
+# conflicts are NOT in them, so frac = t_roof / t_measured charges all of that to the kernel.
+#   key-order walk (dense complex64 table, keyorder.cuh): parity word = 2 LDS + 1 XOR; flip masks 2 LDS.128;
+#     per group: entry offset 2, LUT LDS.64, zero test, address LOP3, predicated LDG.64, 2 F2F, 2 DFMA = 10 instr,
+#     1 (16-entry LUT) or 2 (64-entry LUT) shared wavefronts + 1 table line
+#   hash walk, light pass (sliced.cuh): parity word = NN LDS + NN/2 XOR; 6 LDS.128 (hashes, zero masks; B: +1 LDS.64);
+#     per group: zero-mask rotate 2, filter offset LOP3, LDS, bit XOR, rotate, 2 LOP3, predicated OR = 9 instr, 1 wavefront;
+#     push: 8 instr, 2 wavefronts.  Survivors (data dependent, ~1.5 % of the pairs at 1e5 keys) are not counted.
+#   big-group word (30 terms): parity word + header, then per 6-term chunk: offset 2, LUT LDS.64, DADD = 4 instr, 2 wavefronts
+ISSUE_PER_CLK_SM, WAVEFRONTS_PER_CLK_SM = 4.0, 1.0  # sm_100a: 4 warp schedulers, one L1TEX data-stage wavefront per clock (ncu peaks)
+
+
+def stream_units(xy_words):
+    """(A records, B records, big-group words, big groups) of a term table, as the stream builders cut it (sliced.cuh / keyorder.cuh)."""
+    a = np.ascontiguousarray(xy_words).reshape(len(xy_words), -1)
+    _, counts = np.unique(a, axis=0, return_counts=True)
+    n_a, n_b, big = int((counts <= 4).sum()), int(((counts > 4) & (counts <= 6)).sum()), counts[counts > 6]
+    return (n_a + 7) // 8, (n_b + 4) // 5, int(((big + 29) // 30).sum()), int(len(big))
+
+
+def pipe_roofline(mode, units, n_warp_units, nn, kernel_ms, sm_mhz, sm_count=148):
+    """t_roof = max(issue, L1TEX) time of the algorithmic work above at the SM clock measured DURING the run; frac = t_roof / t_kernel."""
+    rec_a, rec_b, words_c, blobs = units
+    if mode == "keyorder":
+        per = {"A": (5 + 8 * 10, 4 + 8 * 2), "B": (4 + 5 * 10, 4 + 5 * 3), "C": (4 + 5 * 4, 3 + 5 * 2), "blob": (8, 1)}
+    else:
+        par_i, par_w = nn + nn // 2, nn
+        per = {"A": (par_i + 6 + 8 * 9 + 8, par_w + 6 + 8 + 2), "B": (par_i + 7 + 5 * 11 + 8, par_w + 7 + 5 + 2),
+               "C": (par_i + 5 * 4, par_w + 5 * 2), "blob": (20, 3)}
+    instr = rec_a * per["A"][0] + rec_b * per["B"][0] + words_c * per["C"][0] + blobs * per["blob"][0]
+    waves = rec_a * per["A"][1] + rec_b * per["B"][1] + words_c * per["C"][1] + blobs * per["blob"][1]
+    clk = sm_mhz * 1e6
+    t_issue = n_warp_units * instr / (ISSUE_PER_CLK_SM * sm_count * clk)
+    t_l1 = n_warp_units * waves / (WAVEFRONTS_PER_CLK_SM * sm_count * clk)
+    t_roof = max(t_issue, t_l1)
+    return {"bound": "l1tex" if t_l1 >= t_issue else "issue", "t_roof_ms": 1e3 * t_roof, "t_issue_ms": 1e3 * t_issue, "t_l1tex_ms": 1e3 * t_l1,
+            "frac": 1e3 * t_roof / kernel_ms, "warp_units": int(n_warp_units), "warp_instr_per_unit": int(instr), "wavefronts_per_unit": int(waves),
+            "formulation": mode, "sm_mhz": sm_mhz, "sm_count": sm_count}
+
+
 def run_reference(args):
     """The reference's own CPU implementation of the path (compiled Cython kernels from oracle/_ref + the numpy/scipy
     orchestration of hamiltonian.py:272-370 restated in oracle/ref_path.py), all host threads, bounded sample per step."""
@@ -539,11 +582,30 @@ def main():
     achieved_gbs = algo_bytes / (k_ms * 1e-3) / 1e9
     ncu = ncu_summary().get(args.workload, {})
     traffic = (ncu.get("dram_bytes_read", 0) + ncu.get("dram_bytes_write", 0)) if ncu else None
-    roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"],
-                "traffic": traffic, "peak_source": peak_src, "kernel": "eloc_sliced_kernel (+ mark_keys / rows_finalize in key-order mode)",
-                "kernel_ms": k_ms, "algorithmic_bytes": int(algo_bytes),
-                "note": "HBM is NOT the binding resource of this path (0.03 B per coupling, SURVEY.md §8d): the kernel is bound by L1TEX "
-                        "wavefronts (shared-memory LUT reads + table gathers) and warp-instruction issue; see roofline_pipe"}
+    roofline_hbm = {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"],
+                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": int(algo_bytes),
+                    "note": "HBM is NOT the binding resource of this path (0.03 B per coupling, SURVEY.md §8d)"}
+    # binding resource: L1TEX wavefronts / warp-instruction issue of the formulation's algorithmic work, computed from THIS run's
+    # kernel time and SM clock (nothing is read from a committed profile)
+    clk_summary = clocks.summary()
+    sm_mhz = float(clk_summary.get("sm_mhz") or clk_summary.get("sm_max_mhz") or 1965.0)
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    keyorder_mode = wl["N"] <= 26 and W == 1 and table_kind == "dense" and (T >= (1 << wl["N"]) // 8)
+    units = stream_units(np.asarray(wl["xy"]))
+    n_units = ((1 << wl["N"]) // 32) if keyorder_mode else (M + 31) // 32
+    nn = 5 if wl["N"] <= 20 else (8 if wl["N"] <= 32 else (16 if wl["N"] <= 63 else 32))
+    pr = pipe_roofline("keyorder" if keyorder_mode else "hash" if table_kind == "hash" else "dense-rows", units, n_units, nn, k_ms, sm_mhz, sm_count)
+    wave_rate = pr["warp_units"] * pr["wavefronts_per_unit"] / (k_ms * 1e-3) / 1e9
+    instr_rate = pr["warp_units"] * pr["warp_instr_per_unit"] / (k_ms * 1e-3) / 1e9
+    l1_bound = pr["bound"] == "l1tex"
+    roofline = {"bound": pr["bound"], "achieved": wave_rate if l1_bound else instr_rate,
+                "peak": (WAVEFRONTS_PER_CLK_SM if l1_bound else ISSUE_PER_CLK_SM) * sm_count * sm_mhz * 1e-3,
+                "unit": "Gwavefront/s" if l1_bound else "Gwarp-instr/s", "frac": pr["frac"], "traffic": traffic,
+                "kernel": ("eloc_keyorder_kernel" if keyorder_mode else "eloc_sliced_kernel") + " (timed with CUDA events around naqs_eloc: includes its mark / bin / finalize helpers)",
+                "kernel_ms": k_ms, "model": pr,
+                "peak_source": "algorithmic wavefronts and warp instructions of the formulation (bench.py pipe_roofline, DESIGN.md §6) against 1 wavefront "
+                               "and 4 warp instructions per clock and SM at the SM clock sampled during this run",
+                "hbm": roofline_hbm}
     pp, pp_name = pipe_peaks()
     kernel_rate = M * K / (k_ms * 1e-3)
     roofline_pipe = {"kernel_couplings_per_s": kernel_rate, "unit": UNIT}
@@ -552,10 +614,8 @@ def main():
                               "vs_direct_ceiling": kernel_rate / pp["direct_couplings_per_s"] if pp.get("direct_couplings_per_s") else None,
                               "popc_ops_per_s": pp.get("popc_ops_per_s"), "dadd_ops_per_s": pp.get("dadd_ops_per_s"),
                               "gather16B_L2_per_s": pp.get("gather16B_16MB_per_s"), "peak_source": f"profiles/{pp_name}"})
-    if ncu:
-        roofline_pipe.update({"bound": "l1tex_wavefronts" if ncu["l1tex_data_pipe_pct"] >= ncu["issue_active_pct"] else "issue",
-                              "l1tex_data_pipe_pct_ncu": ncu["l1tex_data_pipe_pct"], "issue_active_pct_ncu": ncu["issue_active_pct"],
-                              "frac": max(ncu["l1tex_data_pipe_pct"], ncu["issue_active_pct"]) / 100.0,
+    if ncu:  # context only: pipe utilisation of the committed ncu capture of this workload (NOT the roofline fraction above)
+        roofline_pipe.update({"l1tex_data_pipe_pct_ncu": ncu["l1tex_data_pipe_pct"], "issue_active_pct_ncu": ncu["issue_active_pct"],
                               "ncu_source": ncu.get("source")})
     extras = None
     if world == 1 and not args.no_extras:
@@ -575,7 +635,7 @@ def main():
             "config": {"workload": wl["desc"], "states_per_gpu": M, "terms": K, "lookup_keys": T,
                        "parallelism": f"states sharded x{world}, Pauli table replicated" + ((", NCCL all-reduce (MAX) of the 2^N-entry complex64 amplitude table" if allreduce_table else ", NCCL all-gather of (key, psi)") + " + all-reduce of 5 fp64 sums" if world > 1 else ""),
                        "l2": "256 MB device memset between timed steps (L2 flush, untimed)", "timing": "CUDA events per step on the launching stream, max over ranks"},
-            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_pipe": roofline_pipe,
+            "clocks": clk_summary, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_pipe": roofline_pipe,
             "cpu_baseline": cpu, "other_configs": extras,
             "check": {"mean_eloc_re": float(stats[1] / stats[0]), "n": int(stats[4])}}
     print(json.dumps(line))

@@ -37,7 +37,8 @@ enum {
     NAQS_ERR_DTYPE = 2,  /* unsupported element type (-> TypeError in the Python shims)     */
     NAQS_ERR_CUDA = 3,   /* CUDA runtime / launch failure, or no device                    */
     NAQS_ERR_ALLOC = 4,  /* out of memory (host or device)                                 */
-    NAQS_ERR_STATE = 5   /* call order violated (e.g. E_loc before a lookup table was set) */
+    NAQS_ERR_STATE = 5,  /* call order violated (e.g. E_loc before a lookup table was set) */
+    NAQS_ERR_INDEX = 6   /* a state index outside [0, 2^n_qubits) (-> IndexError in the Python shims) */
 };
 
 /* psi element types of naqs_lookup_build / naqs_eloc */
@@ -101,7 +102,7 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
  *   4. naqs_lookup_attach_dense32: naqs_eloc / naqs_apply_h then read this table (key-order walk).
  * The table must stay alive until the next naqs_lookup_build / attach, and its address must be a multiple of its size
  * (8 * 2^n bytes): the kernel forms entry addresses with XORs, (base ^ key * 8) ^ (flip * 8). */
-int naqs_dense32_scatter(float* d_table /* [2^n][2] */, const uint64_t* d_keys, const void* d_psi_c64, int64_t n_keys, void* stream);
+int naqs_dense32_scatter(float* d_table, int64_t entries, const uint64_t* d_keys, const void* d_psi, int64_t n, void* stream);
 int naqs_lookup_attach_dense32(naqs_table_t* t, const float* d_table, int64_t n_entries);
 
 /* ------------------------------------------------------------------------------------------
@@ -136,6 +137,13 @@ int naqs_table_set_algo(naqs_table_t* t, int algo);
  * complex64 there, sparse_math.pyx:13-41) — within float32 rounding of it.  A float32 table runs the direct formulation.
  * bits other than 32 / 64 (np.float128) -> NAQS_ERR_DTYPE. */
 int naqs_table_set_precision(naqs_table_t* t, int bits);
+
+/* Key range errors.  A state index with bits at or above n_qubits is not an index at all: the reference fails with IndexError
+ * when it reaches hilbert.py:607-640 (full2restricted_idx indexes a 2^N lookup table) or scipy's H[idx[:,None], idx]
+ * (hamiltonian.py:94).  The device path never uses such a key as an address: it is left out of the lookup table, its own row is
+ * NaN, and a flag is raised that this call reports (NAQS_ERR_INDEX) and clears.  Synchronises `stream`.  naqs_eloc_host
+ * performs the check itself. */
+int naqs_table_check(naqs_table_t* t, void* stream);
 
 /* Same through HOST buffers (what a caller holding numpy arrays / CPU tensors uses; bench.py's e2e leg): uploads
  * states + psi, builds the lookup table, runs naqs_eloc and downloads E_loc.  Synchronous.
@@ -204,6 +212,17 @@ int naqs_restricted_index(naqs_table_t* t, const uint64_t* d_keys, int64_t n, in
  * out5 = [sum w, sum w*Re E, sum w*Im E, sum w*(Re E)^2, n].  d_w may be NULL (w = 1).
  * These five numbers are what the multi-GPU path all-reduces. */
 int naqs_eloc_stats(naqs_table_t* t, const double* d_eloc, const double* d_w, int64_t n, double* d_out5, void* stream);
+/* Loss terms of one VMC step (src/optimizer/energy.py:316-329, 367-375) from E_loc and the five sums above — the sums of
+ * THIS rank, or the all-reduced ones when the batch is sharded — in fp64, results as float32 pairs like the tensors the
+ * reference's loss sees (src/utils/complex.py:139-140):
+ *   d_eloc_f32      [n][2]  E_loc truncated to float32 (what calculate_local_energy returns)             or NULL
+ *   d_eloc_corr_f32 [n][2]  E_loc - (sum w E)/(sum w)           (e_loc_corr, energy.py:328)                or NULL
+ *   d_grad_w_f32    [n][2]  2 w_i/(sum w) * conj(e_loc_corr_i): exp_op = sum_i <log_psi_i, grad_w_i> — the detached
+ *                            weight vector autograd needs (energy.py:329)                                  or NULL
+ *   d_energy_var    [3]     Re mean, Im mean, variance of Re E   (energy.py:372-375)                       or NULL
+ * d_w: the (unnormalised) sample weights, NULL = 1. */
+int naqs_loss_terms(const double* d_eloc, const double* d_w, int64_t n, const double* d_sums5, float* d_eloc_f32, float* d_eloc_corr_f32,
+                    float* d_grad_w_f32, double* d_energy_var, void* stream);
 
 #ifdef __cplusplus
 }

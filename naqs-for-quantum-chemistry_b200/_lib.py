@@ -16,7 +16,7 @@ NAQS_C128, NAQS_C64 = 0, 1
 LOOKUP_AUTO, LOOKUP_DENSE, LOOKUP_HASH = 0, 1, 2
 LOOKUP_ASSUME_UNIQUE = 0x100
 LOOKUP_DUPLICATES_EQUAL = 0x200
-_OK, _ERR_ARG, _ERR_DTYPE, _ERR_CUDA, _ERR_ALLOC, _ERR_STATE = range(6)
+_OK, _ERR_ARG, _ERR_DTYPE, _ERR_CUDA, _ERR_ALLOC, _ERR_STATE, _ERR_INDEX = range(7)
 
 # every symbol include/naqs_eloc.h declares: (restype, argtypes)
 _p, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
@@ -33,9 +33,10 @@ SIGNATURES = {
     "naqs_table_set_algo": (_i, [_p, _i]),
     "naqs_table_set_precision": (_i, [_p, _i]),
     "naqs_apply_h": (_i, [_p, _p, _i64, _p, _p]),
-    "naqs_dense32_scatter": (_i, [_p, _p, _p, _i64, _p]),
+    "naqs_dense32_scatter": (_i, [_p, _i64, _p, _p, _i64, _p]),
     "naqs_lookup_attach_dense32": (_i, [_p, _p, _i64]),
     "naqs_eloc_host": (_i, [_p, _p, _i, _p, _i, _i64, _p, _p, _i64, _i, _p, _i]),
+    "naqs_table_check": (_i, [_p, _p]),
     "naqs_rows_count": (_i, [_p, _p, _i64, _p, _p]),
     "naqs_exclusive_scan": (_i, [_p, _p, _i64, _p, _p]),
     "naqs_rows_fill": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p]),
@@ -49,6 +50,7 @@ SIGNATURES = {
     "naqs_state2idx": (_i, [_p, _i64, _i, _i, _p, _p]),
     "naqs_restricted_index": (_i, [_p, _p, _i64, _p, _p]),
     "naqs_eloc_stats": (_i, [_p, _p, _p, _i64, _p, _p]),
+    "naqs_loss_terms": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p, _p]),
 }
 
 
@@ -94,6 +96,8 @@ def check(rc, what=""):
         raise TypeError(msg)
     if rc == _ERR_ARG:
         raise ValueError(msg)
+    if rc == _ERR_INDEX:
+        raise IndexError(msg)
     raise NaqsError(f"{what or 'libnaqs_eloc'}: {msg} (status {rc})")
 
 

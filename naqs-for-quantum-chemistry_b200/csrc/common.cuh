@@ -169,9 +169,10 @@ __host__ __device__ inline unsigned long long hash_slot(unsigned long long k0, u
 
 // Bloom filter of the hash lookups.  In a sparse VMC batch almost every coupled state is NOT in the table; the filter
 // answers those without the global sector read of a bucket / slot.  Blocked: both bits of a key live in ONE 32-bit word
-// (one load per test).  2^14 words (64 KB, >= 4 bits per key) up to 2^17 keys — that size is copied into shared memory by
-// every CTA of the 1024-thread launch shape and consulted for every (state, group) pair; larger batches get >= 16 bits
-// per key, up to 2^22 words (16 MB, L2-resident), consulted from global memory before a bucket / slot probe.
+// (one load per test).  2^15 words (128 KB, >= 4 bits per key) up to 2^18 keys — that size is copied into shared memory by
+// every CTA of the 1024-thread launch shape and consulted for every (state, group) pair (about 2 % false positives at
+// 1e5 keys: three bits per key); larger batches get >= 16 bits per key, up to 2^22 words (16 MB, L2-resident),
+// consulted from global memory before a bucket / slot probe.
 //
 // The hashes are GF(2)-LINEAR in the key (XOR of one pseudo-random 64-bit column per set key bit): hash(s ^ u) =
 // hash(s) ^ hash(u), so the fused kernel keeps hash(s) per thread, reads hash(u) with the group's flip mask (warp-uniform)
@@ -180,11 +181,11 @@ __host__ __device__ inline unsigned long long hash_slot(unsigned long long k0, u
 // filter word is bits 2..6 of the word hash, so bank(s ^ u) = bank(s) ^ bank(u) — a warp whose 32 states have pairwise
 // different bank(s) probes 32 different banks for EVERY group (bin_states_kernel arranges the batch that way).
 //   hw: byte offset of the filter word (bits 0-1 clear; a filter of 2^L words uses hw & (4 * 2^L - 4))
-//   hb: low 5 bits = position b of the key's first bit; the second bit sits 13 positions further (mod 32):
-//       set  word |= rotl(0x2001, b),   test  (~rotr(word, b) & 0x2001) == 0
-constexpr int kFilterLog2WordsSmem = 14, kFilterLog2WordsMax = 22;
+//   hb: low 5 bits = position b of the key's first bit; the other two sit 11 and 21 positions further (mod 32):
+//       set  word |= rotl(kFilterPattern, b),   test  (~rotr(word, b) & kFilterPattern) == 0
+constexpr int kFilterLog2WordsSmem = 15, kFilterLog2WordsMax = 22;
 constexpr uint32_t kFilterBytes = (1u << kFilterLog2WordsSmem) * 4;  // the shared-memory copy
-constexpr uint32_t kFilterPattern = 0x2001u;
+constexpr uint32_t kFilterPattern = 0x00200801u;  // bits 0, 11, 21
 __host__ __device__ inline void lin_hash_word(uint32_t x, int word_index, uint32_t& hw, uint32_t& hb) {
     while (x) {
 #ifdef __CUDA_ARCH__
@@ -279,7 +280,8 @@ struct naqs_table {
     int* d_flags = nullptr;   // [4] device flags (bit 0 of [0]: key out of range), see naqs_table_check
     int32_t* d_perm = nullptr;      // bank-binned order of a hash-lookup batch (bin_states_kernel) + 33 counters in front
     size_t perm_bytes = 0;
-    bool env_no_bin = false;
+    bool env_no_bin = false, env_static_tasks = false;
+    int env_chunks = 0;
 
     naqs::TableView view() const { return naqs::TableView{d_yz, d_coeff, d_gxy, d_gstart, (int)K, (int)G, f32}; }
     naqs::LookupView lookup() const {

@@ -198,6 +198,33 @@ int run_spsmv(const void* data, const void* indices, const void* indptr, int idx
 
 }  // namespace
 
+// Loss statistics of one VMC step from E_loc and the (reduced) five sums (src/optimizer/energy.py:316-329, 367-375), fp64:
+//   mean = (sum w E) / (sum w)                         the weighted complex mean subtracted at energy.py:328
+//   e_loc_corr_i = E_i - mean
+//   grad_w_i = 2 w_i / (sum w) * conj(e_loc_corr_i)     so that  exp_op = sum_i Re(log_psi_i * 2 w_i e_loc_corr_i)
+//                                                                   = sum_i (Re log_psi_i * grad_w_i.x + Im log_psi_i * grad_w_i.y):
+//                                                       autograd only needs this detached weight vector (energy.py:329)
+//   energy = Re mean,  variance = sum w (Re E - energy)^2 / sum w = (sum w (Re E)^2) / (sum w) - energy^2   (energy.py:372-375)
+// Outputs are float32 pairs like the tensors the reference's loss sees (complex.py:139-140); any of them may be NULL.
+__global__ void loss_terms_kernel(const double2* __restrict__ eloc, const double* __restrict__ w, int64_t n, const double* __restrict__ sums5,
+                                  float2* __restrict__ eloc32, float2* __restrict__ corr32, float2* __restrict__ gradw32, double* __restrict__ energy_var) {
+    const double sw = sums5[0];
+    const double mean_re = sums5[1] / sw, mean_im = sums5[2] / sw;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && energy_var) {
+        energy_var[0] = mean_re;
+        energy_var[1] = mean_im;
+        energy_var[2] = sums5[3] / sw - mean_re * mean_re;
+    }
+    if (i >= n) return;
+    const double2 e = eloc[i];
+    const double wi = (w ? w[i] : 1.0) / sw;
+    const double cr = e.x - mean_re, ci = e.y - mean_im;
+    if (eloc32) eloc32[i] = make_float2((float)e.x, (float)e.y);
+    if (corr32) corr32[i] = make_float2((float)cr, (float)ci);
+    if (gradw32) gradw32[i] = make_float2((float)(2.0 * wi * cr), (float)(-2.0 * wi * ci));
+}
+
 extern "C" {
 
 int naqs_popcount_parity(const void* d_in, int itemsize, int64_t n, int8_t* d_out, void* stream) {
@@ -290,6 +317,17 @@ int naqs_state2idx(const int8_t* d_states, int64_t M, int n_qubits, int words, u
     if (M == 0) return NAQS_OK;
     const int64_t warps = std::min<int64_t>(M, 148 * 64);
     state2idx_kernel<<<blocks_for(warps * 32), 256, 0, (cudaStream_t)stream>>>(d_states, M, n_qubits, words, d_keys);
+    NAQS_LAUNCHED();
+    return NAQS_OK;
+}
+
+int naqs_loss_terms(const double* d_eloc, const double* d_w, int64_t n, const double* d_sums5, float* d_eloc_f32, float* d_eloc_corr_f32,
+                    float* d_grad_w_f32, double* d_energy_var, void* stream) {
+    NAQS_REQUIRE(n >= 0 && d_sums5 && (n == 0 || d_eloc), NAQS_ERR_ARG, "naqs_loss_terms: NULL buffers");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned blocks = (unsigned)std::max<int64_t>(1, (n + 255) / 256);
+    loss_terms_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const double2*>(d_eloc), d_w, n, d_sums5, reinterpret_cast<float2*>(d_eloc_f32),
+                                              reinterpret_cast<float2*>(d_eloc_corr_f32), reinterpret_cast<float2*>(d_grad_w_f32), d_energy_var);
     NAQS_LAUNCHED();
     return NAQS_OK;
 }

@@ -17,15 +17,19 @@
 // fully serial order and is bit-exact for every group.
 //
 // Stream layout (device memory, staged into shared memory tile by tile with cp.async.bulk + mbarrier):
-//   A record (8 groups x 4 bits):  T[NN][16] u32 | U[8][NW] u32 (+ U << 3 when NW == 1) | HW[8] HB[8] u32 | LUT[8][16] f64
-//   B record (5 groups x 6 bits):  T[NN][16] u32 | U[8][NW] u32 (+ U << 3 when NW == 1) | HW[8] HB[8] u32 | LUT[5][64] f64
+//   A record (8 groups x 4 bits):  T[NN][16] u32 | U[8][NW] u32 (+ U << 3 when NW == 1) | HW[8] HB[8] u32 | Z[16] u32 | LUT[8][16] f64
+//   B record (5 groups x 6 bits):  T[NN][16] u32 | U[8][NW] u32 (+ U << 3 when NW == 1) | HW[8] HB[8] u32 | Z[16] u32 | LUT[5][64] f64
 //   C blob   (<= 150 terms of one big group; a longer group is several blobs with the same u, each contributing
 //             H_blob * psi(s ^ u) on its own):  header{n_words, HW, HB, -, u[4]} | n_words x ( T[NN][16] u32 | LUT[5][64] f64 )
 //   HW / HB: the GF(2)-linear Bloom-filter hashes of the flip mask u (lin_hash, common.cuh).  Linear means
 //   hash(s ^ u) = hash(s) ^ hash(u): the filter test of a coupled state costs two XORs with the per-thread hash(s).
+//   Z: which LUT entries are NOT exactly 0.0 — all the light pass of the hash walk needs from H (hamiltonian.py:363):
+//   A: Z[j] = 16-bit mask of group j in both halves of the word (a rotate by the group's parity bits, whatever sits in
+//   bit 4 of the amount, lands on the entry's flag); B: Z[2j], Z[2j+1] = low / high half of group j's 64-bit mask.
 #pragma once
 #include <algorithm>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -60,7 +64,7 @@ struct HostGroup {
 inline int nibbles_for(int n_qubits) { return n_qubits <= 20 ? 5 : (n_qubits <= 32 ? 8 : (n_qubits <= 63 ? 16 : 32)); }
 // flip masks of a record: 8 slots of nw words; single-word keys carry a second copy shifted left by 3 (= byte offsets into
 // the complex64 direct-address table, whose base is aligned to its size: entry address = (base ^ key * 8) ^ (u * 8))
-inline size_t u_bytes(int nw) { return (nw == 1 ? 64 : (size_t)32 * nw) + 64; }  // masks + their filter hashes HW[8], HB[8]
+inline size_t u_bytes(int nw) { return (nw == 1 ? 64 : (size_t)32 * nw) + 128; }  // masks + their filter hashes HW[8], HB[8] + zero masks Z[16]
 inline size_t rec_bytes_A(int nn, int nw) { return (size_t)64 * nn + u_bytes(nw) + 8 * 16 * 8; }
 inline size_t rec_bytes_B(int nn, int nw) { return (size_t)64 * nn + u_bytes(nw) + 5 * 64 * 8; }
 inline size_t rec_bytes_C(int nn) { return (size_t)64 * nn + 5 * 64 * 8; }  // one word of a big group: 5 chunks of <= 6 terms
@@ -128,13 +132,17 @@ inline void build_sliced_host(const std::vector<HostGroup>& groups, int n_qubits
                 for (int t = 0; t < n; ++t) yz_of_bit[j * bits + t] = g->yz.data() + (size_t)t * nw;
                 for (int w = 0; w < nw; ++w) U[j * nw + w] = g ? g->u[w] : 0u;
                 if (nw == 1) U[8 + j] = g ? g->u[0] << 3 : 0u;
+                for (unsigned pat = 0; pat < (1u << bits); ++pat) L[j * (1 << bits) + pat] = g ? lut_entry(g->c.data(), n, pat) : 0.0;
                 {
-                    uint32_t* HWB = reinterpret_cast<uint32_t*>(p + 64 * nn + u_bytes(nw) - 64);
+                    uint32_t* HWB = reinterpret_cast<uint32_t*>(p + 64 * nn + u_bytes(nw) - 128);
                     uint32_t hw = 0, hb = 0;
                     if (g) for (int w = 0; w < nw; ++w) lin_hash_word(g->u[w], w, hw, hb);
                     HWB[j] = hw; HWB[8 + j] = hb;
+                    uint64_t z = 0;  // bit e: LUT entry e of this group is not exactly 0.0
+                    for (unsigned pat = 0; pat < (1u << bits); ++pat) z |= (uint64_t)(L[j * (1 << bits) + pat] != 0.0) << pat;
+                    if (bits == 4) HWB[16 + j] = (uint32_t)z | ((uint32_t)z << 16);
+                    else { HWB[16 + 2 * j] = (uint32_t)z; HWB[16 + 2 * j + 1] = (uint32_t)(z >> 32); }
                 }
-                for (unsigned pat = 0; pat < (1u << bits); ++pat) L[j * (1 << bits) + pat] = g ? lut_entry(g->c.data(), n, pat) : 0.0;
             }
             fill_nibble_tables(p, nn, nw, yz_of_bit, per * bits);
         }
@@ -304,19 +312,23 @@ __device__ __forceinline__ void emit_batch(const double (&h)[B], const uint32_t 
     }
 }
 
-// Bloom-filter test of a coupled state (launch shape with the filter in shared memory): a clear bit proves the key is not
-// in the table — ~90 % of the couplings of a large-sector batch end here without touching global memory.  Cheap enough
-// (one LDS, two IMAD, a few shifts) to run for EVERY (state, group) pair in the light path, before anything is queued.
-// The same test against the filter in GLOBAL memory (larger batches, or shapes without room for the copy) runs in the
-// probe rounds, where it replaces most bucket reads (HBM sectors of a table far larger than L2) by L2 hits.
-template <int NW>
-__device__ __forceinline__ bool filter_pass(const uint32_t (&j)[NW], const uint32_t* __restrict__ filt, int wshift) {
-    unsigned long long k0, k1;
-    key_words64<NW>(j, k0, k1);
-    uint32_t w, b1, b2;
-    filter_word_bits(k0, k1, hash32(k0, k1), wshift, w, b1, b2);
-    const uint32_t word = filt[w];
-    return ((word >> b1) & (word >> b2) & 1u) != 0;
+// Bloom-filter test of a coupled state s ^ u from the linear hashes (xw, xb) = hash(s) ^ hash(u) (common.cuh): a clear bit
+// proves the key is not in the table — ~90 % of the couplings of a large-sector batch end here without touching global
+// memory.  `filt` is indexed in BYTES; mask = 4 * n_words - 4.
+// mask |= bit  iff  every pattern bit of r (the rotated filter word) is set AND bit 0 of t (the rotated zero mask) is set.
+// Spelled in PTX so that it stays two LOP3 + compare + predicated OR (ptxas otherwise expands it into two compare / select chains).
+__device__ __forceinline__ void survivor_bit(uint32_t& mask, uint32_t r, uint32_t t, uint32_t bit) {
+    asm("{\n .reg .b32 a, v;\n .reg .pred p;\n"
+        " lop3.b32 a, %1, %2, 0, 0x0c;\n"   // a = ~r & pattern
+        " lop3.b32 v, a, %3, 1, 0xf2;\n"    // v = a | (~t & 1)
+        " setp.eq.u32 p, v, 0;\n"
+        " @p or.b32 %0, %0, %4;\n}"
+        : "+r"(mask) : "r"(r), "r"(kFilterPattern), "r"(t), "r"(bit));
+}
+
+__device__ __forceinline__ bool filter_pass(uint32_t xw, uint32_t xb, const unsigned char* __restrict__ filt, uint32_t mask) {
+    const uint32_t word = *reinterpret_cast<const uint32_t*>(filt + (xw & mask));
+    return (~__funnelshift_r(word, word, xb) & kFilterPattern) == 0u;  // rotate right by xb & 31: the key's bits land on the pattern
 }
 
 // Hash-lookup ("heavy") epilogue of up to B couplings of one thread: optional Bloom-filter test (`filt`: the filter in
@@ -326,10 +338,11 @@ __device__ __forceinline__ bool filter_pass(const uint32_t (&j)[NW], const uint3
 // whose coupled state passed the filter — which the per-thread queue of the kernel below makes dense across the warp.
 // The first probes of all B couplings are issued before any is examined, so their L2 latencies overlap.  SEC: sector test
 // on the coupled state (hamiltonian.py:328); unused by the library's own tables, which hold in-sector keys only.
+// (xw, xb)[b]: linear filter hashes of the coupled state.
 template <int NW, bool SEC, int B>
-__device__ __forceinline__ void heavy_lookup(int n, const double (&h)[B], const uint32_t* const (&u)[B], const uint32_t (&s)[NW],
-                                             const Sector& sec, const LookupView& lv, const uint32_t* __restrict__ filt, int filt_wshift,
-                                             double& e_re, double& e_im) {
+__device__ __forceinline__ void heavy_lookup(int n, const double (&h)[B], const uint32_t* const (&u)[B], const uint32_t (&xw)[B], const uint32_t (&xb)[B],
+                                             const uint32_t (&s)[NW], const Sector& sec, const LookupView& lv, const unsigned char* __restrict__ filt,
+                                             uint32_t filt_mask, double& e_re, double& e_im) {
     unsigned long long k0[B], k1[B];
     unsigned slot[B];
     bool on[B];
@@ -341,7 +354,7 @@ __device__ __forceinline__ void heavy_lookup(int n, const double (&h)[B], const 
         for (int w = 0; w < NW; ++w) j[w] = on[b] ? (s[w] ^ u[b][w]) : s[w];
         if constexpr (SEC) on[b] = on[b] & in_sector<NW>(j, sec);
         key_words64<NW>(j, k0[b], k1[b]);
-        if (filt) on[b] = on[b] & filter_pass<NW>(j, filt, filt_wshift);  // a clear bit proves the key is not in the table
+        if (filt) on[b] = on[b] & filter_pass(xw[b], xb[b], filt, filt_mask);  // a clear bit proves the key is not in the table
         if constexpr (NW <= 2) slot[b] = hash32(k0[b], 0ull) >> lv.bshift;
         else slot[b] = (unsigned)hash_slot(k0[b], k1[b], lv.shift);
     }
@@ -390,44 +403,77 @@ __device__ __forceinline__ void heavy_lookup(int n, const double (&h)[B], const 
     }
 }
 
-constexpr int kQueueCap = 16;  // pending couplings per thread (hash mode)
+// pending RECORDS per thread (hash mode): 8-byte entries {parity word, survivor mask | record}; a ring (FIFO), so a thread
+// resolves its couplings in record order whatever the rest of its warp does — E_loc is reproducible bit for bit
+constexpr int kQueueCap = 8, kQueueCapFilter = 4;  // without / with the filter in shared memory (survivors: ~60 % / ~1.5 % of the pairs)
 
-// One state per thread.  Each CTA owns state blocks blockIdx.x, blockIdx.x + gridDim.x, ... and walks the
-// tiles [tile_lo, tile_hi) of its chunk (blockIdx.y) for each of them; with a single tile the table stays
-// resident in shared memory for the CTA's lifetime.
+// Bank-binned order of a hash-lookup batch (bin_states_kernel): position p holds row perm[p] (-1 = empty); the first
+// `base` positions are 32-wide rows whose lane l holds a state with filter bank l, the rest is the overflow of full bins.
+struct BinView {
+    const int32_t* perm;      // nullptr: rows are walked in their own order
+    const int32_t* counters;  // [33]: states per bank, [32] = overflow count
+    int64_t base;
+};
+
+template <int NW>
+__device__ __forceinline__ bool key_in_range(const uint32_t (&s)[NW], int n_qubits) {
+    const int w = n_qubits >> 5, r = n_qubits & 31;
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        if (i > w) ok = ok && s[i] == 0u;
+        else if (i == w) ok = ok && (s[i] >> r) == 0u;
+    }
+    return ok;
+}
+
+// One state per thread.  Work is cut into TASKS = (table chunk, state block), chunk-major: task = chunk * n_blocks + block.
+// A CTA walks the tiles [tile_lo, tile_hi) of the task's chunk for the task's block of states; with a single tile per chunk
+// the table stays resident in shared memory while the chunk does not change.  Tasks are dealt statically (CTA i takes tasks
+// i, i + gridDim.x, ...) or, when `task_counter` is given, dynamically from an atomic counter — the hash walk's tasks differ
+// in length (survivors, overflowing buckets), and with dynamic dealing the launch ends within one task of the ideal.
 //
 // KEYORDER (dense lookup, batch dense in key space): thread m IS key m (states == nullptr, M = 2^N); `need` is a bitmap
 // of the keys that occur as rows; the raw sums S[k] = sum_u H[k, k^u] psi(k^u) go to partial[chunk * M + k] and
 // eloc_rows_finalize_kernel turns them into E_loc per row.  A warp then holds 32 consecutive keys and every table
 // read of a group falls into one aligned 512-byte block: 4 L1 lines per request instead of ~11 scattered sectors.
+//
+// Hash lookup (LK == kLookHash), the sparse-batch case (a VMC batch of a large sector): almost every coupled state is NOT
+// in the table, so the walk is split into a LIGHT pass over every (state, group) pair — H from the group LUT, exact-zero
+// test (hamiltonian.py:363), Bloom-filter test in shared memory from linear hashes (two XORs, one LDS, one rotate) — that
+// only records, per record of 8 (5) groups, a bit mask of the survivors, and a HEAVY pass that resolves the survivors
+// (a few % of the pairs) against the bucketed table in global memory, one coupling per lane and round, from a per-thread
+// queue of {parity word, survivor mask | record offset} entries.
 template <int NW, int NN, int THREADS, int CTAS_PER_SM, int LK, bool SEC, bool KEYORDER, bool PSI32>
 __global__ void __launch_bounds__(THREADS, CTAS_PER_SM)
-eloc_sliced_kernel(SlicedView sv, const __grid_constant__ ChunkBounds chunks, uint32_t buf_bytes, uint32_t queue_offset, uint32_t filter_offset, Sector sec, LookupView lv,
+eloc_sliced_kernel(SlicedView sv, const __grid_constant__ ChunkBounds chunks, uint32_t buf_bytes, uint32_t queue_offset, uint32_t queue_cap, uint32_t filter_offset, Sector sec, LookupView lv,
                    const uint64_t* __restrict__ states, const uint32_t* __restrict__ need, const void* __restrict__ psi,
-                   int psi_dtype, int64_t M, double2* __restrict__ out, double2* __restrict__ partial) {
+                   int psi_dtype, int64_t M, BinView bin, int n_chunks, int* __restrict__ task_counter, double2* __restrict__ out,
+                   double2* __restrict__ partial) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t mbar[2];
-    constexpr int UB = NW == 1 ? 64 : 32 * NW;  // u_bytes(NW)
+    __shared__ int64_t s_task;
+    constexpr int UB = (NW == 1 ? 64 : 32 * NW) + 128;  // u_bytes(NW): flip masks, their filter hashes HW[8] HB[8], zero masks Z[16]
+    constexpr int HOFF = UB - 128, ZOFF = UB - 64;
     constexpr int REC_A = 64 * NN + UB + 1024, REC_B = 64 * NN + UB + 2560, REC_C = 64 * NN + 2560;
+    static_assert(REC_A % 16 == 0 && REC_B % 16 == 0, "queue entries address records in 16-byte units");
 
-    const int tile_lo = chunks.lo[blockIdx.y], tile_hi = chunks.lo[blockIdx.y + 1];
-    const bool resident = (tile_hi - tile_lo) <= 1;
     if (threadIdx.x == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    const uint32_t* sfilt = nullptr;  // Bloom filter of the table keys in shared memory (hash lookup, 1024-thread shape, <= 2^17 keys)
-    const uint32_t* gfilt = nullptr;  // ... or in global memory (L2), consulted in the probe rounds
+    const unsigned char* sfilt = nullptr;  // Bloom filter of the table keys in shared memory (hash lookup, 1024-thread shape, <= 2.5 * 2^18 keys)
+    const unsigned char* gfilt = nullptr;  // ... or in global memory (L2), consulted in the probe rounds
     if constexpr (LK == kLookHash) {
         if (lv.filter && lv.filter_in_smem) {
             uint4* dst = reinterpret_cast<uint4*>(smem + filter_offset);
             const uint4* src = reinterpret_cast<const uint4*>(lv.filter_small ? lv.filter_small : lv.filter);
             for (uint32_t i = threadIdx.x; i < kFilterBytes / 16; i += THREADS) dst[i] = __ldg(src + i);
-            sfilt = reinterpret_cast<const uint32_t*>(smem + filter_offset);
-            if (lv.filter_small) gfilt = lv.filter;  // the full-size filter screens the survivors once more before a bucket read
+            sfilt = smem + filter_offset;
+            if (lv.filter_small) gfilt = reinterpret_cast<const unsigned char*>(lv.filter);  // the full-size filter screens the survivors once more before a bucket read
         } else {
-            gfilt = lv.filter;
+            gfilt = reinterpret_cast<const unsigned char*>(lv.filter);
         }
     }
     __syncthreads();
@@ -437,7 +483,7 @@ eloc_sliced_kernel(SlicedView sv, const __grid_constant__ ChunkBounds chunks, ui
     Sector sec8 = sec;
     sec8.even[0] <<= 3; sec8.odd[0] <<= 3;
     uint32_t phase0 = 0, phase1 = 0;
-    bool have_resident = false;
+    int resident_chunk = -1;  // chunk whose single tile currently sits in buffer 0
 
     auto issue = [&](int t, int b) {  // thread 0 only
         const STile tl = sv.tiles[t];
@@ -445,10 +491,30 @@ eloc_sliced_kernel(SlicedView sv, const __grid_constant__ ChunkBounds chunks, ui
         bulk_g2s(smem + (size_t)b * buf_bytes, sv.stream + tl.offset, tl.bytes, &mbar[b]);
     };
 
-    const int64_t n_blocks = (M + THREADS - 1) / THREADS;
-    for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        const int64_t m = blk * THREADS + threadIdx.x;
-        bool valid = m < M;
+    // positions to walk: the rows themselves, or the bank-binned arrangement of them (hash lookup with the filter in shared memory)
+    const int64_t n_pos = bin.perm ? bin.base + (int64_t)__ldg(bin.counters + 32) : M;
+    const int64_t n_blocks = (n_pos + THREADS - 1) / THREADS;
+    const int64_t n_tasks = n_blocks * n_chunks;
+    for (int64_t task = blockIdx.x;; task += gridDim.x) {
+        if (task_counter) {  // dynamic dealing
+            __syncthreads();  // everyone is done with s_task of the previous round
+            if (threadIdx.x == 0) s_task = (int64_t)atomicAdd(task_counter, 1);
+            __syncthreads();
+            task = s_task;
+        }
+        if (task >= n_tasks) break;
+        const int chunk = (int)(task / n_blocks);
+        const int64_t blk = task - (int64_t)chunk * n_blocks;
+        const int tile_lo = chunks.lo[chunk], tile_hi = chunks.lo[chunk + 1];
+        const bool resident = (tile_hi - tile_lo) <= 1;
+        const bool have_resident = resident && resident_chunk == chunk;
+        int64_t m = blk * THREADS + threadIdx.x;
+        bool valid = m < n_pos;
+        if (bin.perm) {
+            const int32_t row = valid ? __ldg(bin.perm + m) : -1;
+            valid = row >= 0;
+            m = row;
+        }
         uint32_t s[NW];
         if constexpr (KEYORDER) {
             s[0] = valid ? (uint32_t)m : 0u;  // threads past the key space read entry 0 (table reads are unconditional)
@@ -456,8 +522,17 @@ eloc_sliced_kernel(SlicedView sv, const __grid_constant__ ChunkBounds chunks, ui
             for (int w = 1; w < NW; ++w) s[w] = 0;
             valid = valid && ((need[m >> 5] >> (m & 31)) & 1u);
         } else {
-            if (valid) load_key<NW>(states, m, s);
-            else {
+            if (valid) {
+                load_key<NW>(states, m, s);
+                if (!key_in_range<NW>(s, sec.n_qubits)) {  // the reference raises IndexError; here: flag (naqs_table_check), row -> NaN
+                    atomicOr(lv.flags, 1);
+                    const double2 nan2 = make_double2(__longlong_as_double(0x7ff8000000000000ll), 0.0);
+                    if (partial) partial[(int64_t)chunk * M + m] = nan2;
+                    else out[m] = nan2;
+                    valid = false;
+                }
+            }
+            if (!valid) {
 #pragma unroll
                 for (int w = 0; w < NW; ++w) s[w] = 0;
             }
@@ -467,69 +542,105 @@ eloc_sliced_kernel(SlicedView sv, const __grid_constant__ ChunkBounds chunks, ui
         const uint32_t a0 = base_lo ^ (s[0] << 3);  // PSI32 only
         double e_re = 0.0, e_im = 0.0;
 
-        // hash mode: a coupling survives the light path when H != 0 AND (filter shape) its coupled state passes the Bloom
-        // filter in shared memory — a few % of the (state, group) pairs of a large-sector batch.  Survivors are parked in a
-        // per-thread queue (shared memory, [slot][thread] layout, one 32-bit word each: LUT byte offset | flip-mask offset
-        // inside the current tile) and resolved in warp-wide rounds, so the expensive part (bucket probe in global memory,
-        // key compare) runs with many lanes busy.  The queue is drained before a tile buffer is released.
-        constexpr uint32_t QSTRIDE = THREADS * 4;  // bytes between consecutive queue slots of one thread
-        unsigned char* const q0 = smem + queue_offset + threadIdx.x * 4;
-        unsigned char* qtail = q0;            // the queue holds (qtail - q0) / QSTRIDE couplings
-        constexpr int PB = 2;  // couplings resolved per thread and round
-        auto pop_round = [&](const unsigned char* __restrict__ buf) {
-            const int n = min((int)((uint32_t)(qtail - q0) / QSTRIDE), PB);
-            double h[PB];
-            const uint32_t* u[PB];
+        // ---- hash mode state: linear filter hashes of the state, the per-thread queue ([slot][thread] layout, 8-byte entries
+        // {P, meta}: P = parity word of the record, meta = survivor mask (bits 0-7) | record offset / 16 (bits 8-19) | B record
+        // (bit 31)) and the entry being resolved.  The queue is drained before a tile buffer is released.
+        [[maybe_unused]] uint32_t hsw = 0, hsb = 0;
+        if constexpr (LK == kLookHash) {
 #pragma unroll
-            for (int b = 0; b < PB; ++b) {
-                // always read a valid slot (the oldest one when the queue is shorter than b + 1): no branch, lanes are masked by n
-                const unsigned char* slot = b < n ? qtail - (b + 1) * QSTRIDE : q0;
-                const uint32_t e = *reinterpret_cast<const uint32_t*>(slot);
-                h[b] = *reinterpret_cast<const double*>(buf + (e & 0xffffu));
-                u[b] = reinterpret_cast<const uint32_t*>(buf + (e >> 16) * 4u);
+            for (int w = 0; w < NW; ++w) lin_hash_word(s[w], w, hsw, hsb);
+        }
+        constexpr uint32_t QSTRIDE = THREADS * 8;  // bytes between consecutive queue slots of one thread
+        unsigned char* const q0 = smem + queue_offset + threadIdx.x * 8;
+        const uint32_t qwrap = queue_cap * QSTRIDE - QSTRIDE;  // ring of queue_cap (a power of two) slots: offset & qwrap
+        uint32_t qhead = 0, qtail = 0;        // byte offsets (multiples of QSTRIDE, free-running); the ring holds (qtail - qhead) / QSTRIDE entries
+        uint32_t cur_P = 0, cur_meta = 0;     // entry being resolved: (cur_meta & 0xff) = couplings still pending
+        // one coupling per lane: take the lowest pending group of the current entry (refilled from the ring when exhausted)
+        auto resolve_round = [&](const unsigned char* __restrict__ buf) {
+            if ((cur_meta & 0xffu) == 0u && qhead != qtail) {
+                const uint2 e = *reinterpret_cast<const uint2*>(q0 + (qhead & qwrap));
+                qhead += QSTRIDE;
+                cur_P = e.x; cur_meta = e.y;
             }
-            qtail -= n * QSTRIDE;
-            heavy_lookup<NW, SEC, PB>(n, h, u, s, sec, lv, gfilt, lv.filter_wshift, e_re, e_im);  // a shared-memory filter was consulted before queueing
+            const uint32_t pend = cur_meta & 0xffu;
+            const int n = pend ? 1 : 0;
+            const uint32_t j = pend ? (uint32_t)__ffs((int)pend) - 1u : 0u;
+            cur_meta = pend ? (cur_meta & (cur_meta - 1u)) : cur_meta;  // clear the lowest pending bit (the borrow stays inside the mask field)
+            const unsigned char* rec = buf + ((cur_meta >> 8) & 0xfffu) * 16u;
+            const uint32_t bits = (cur_meta >> 31) ? 6u : 4u;
+            const uint32_t idx = (cur_P >> (j * bits)) & ((1u << bits) - 1u);
+            const double h[1] = {*reinterpret_cast<const double*>(rec + 64 * NN + UB + (((j << bits) + idx) << 3))};
+            const uint32_t* U = reinterpret_cast<const uint32_t*>(rec + 64 * NN);
+            const uint32_t* HWB = reinterpret_cast<const uint32_t*>(rec + 64 * NN + HOFF);
+            const uint32_t* u[1] = {U + j * NW};
+            const uint32_t xw[1] = {hsw ^ HWB[j]}, xb[1] = {hsb ^ HWB[8 + j]};
+            heavy_lookup<NW, SEC, 1>(n, h, u, xw, xb, s, sec, lv, gfilt, lv.filter_mask, e_re, e_im);  // a shared-memory filter was consulted before queueing
         };
+        auto pending = [&]() { return qhead != qtail || (cur_meta & 0xffu) != 0u; };
         auto drain = [&](const unsigned char* __restrict__ buf) {  // before a tile buffer is released: its offsets die with it
-            while (__any_sync(0xffffffffu, qtail != q0)) pop_round(buf);
+            while (__any_sync(0xffffffffu, pending())) resolve_round(buf);
         };
-        // branch-free: the entry is always written at the tail, the tail only advances for a live coupling
         const uint32_t q_adv = valid ? QSTRIDE : 0u;  // an invalid lane never keeps an entry
-        auto push = [&](double h, uint32_t entry) {
-            *reinterpret_cast<uint32_t*>(qtail) = entry;
-            qtail += (h != 0.0) ? q_adv : 0u;
-        };
-        // the same with the shared-memory Bloom filter consulted first; U = the record's flip masks, group j
-        auto push_filtered = [&](double h, const uint32_t* __restrict__ U, int j, const uint4& ua, const uint4& ub, uint32_t entry) {
-            *reinterpret_cast<uint32_t*>(qtail) = entry;
-            uint32_t k[NW];
-            if constexpr (NW == 1) {        // masks of the 8 groups preloaded as two vectors
-                const uint32_t uv[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
-                k[0] = s[0] ^ uv[j];
-            } else if constexpr (NW == 2) {
-                const uint2 v = reinterpret_cast<const uint2*>(U)[j];
-                k[0] = s[0] ^ v.x; k[1] = s[1] ^ v.y;
-            } else {
-                const uint4 v = reinterpret_cast<const uint4*>(U)[j];
-                k[0] = s[0] ^ v.x; k[1] = s[1] ^ v.y; k[2] = s[2] ^ v.z; k[3] = s[3] ^ v.w;
+        // light pass over one record: survivor mask of its groups (H != 0 and, with the filter in shared memory, filter passed).
+        // Nothing of H itself is read: bit `entry` of the group's zero mask Z says whether the LUT entry is exactly 0.0.
+        auto light_record = [&](const unsigned char* __restrict__ buf, const unsigned char* __restrict__ rec, uint32_t rec_meta, auto kind_tag) {
+            constexpr bool KB = decltype(kind_tag)::value;
+            constexpr int G = KB ? 5 : 8, LB = KB ? 6 : 4;
+            const uint32_t P = parity_word<NN>(rec, nib);
+            const uint32_t* Z = reinterpret_cast<const uint32_t*>(rec + 64 * NN + ZOFF);
+            uint32_t z[10];
+            {
+                const uint4 za = *reinterpret_cast<const uint4*>(Z), zb = *reinterpret_cast<const uint4*>(Z + 4);
+                z[0] = za.x; z[1] = za.y; z[2] = za.z; z[3] = za.w; z[4] = zb.x; z[5] = zb.y; z[6] = zb.z; z[7] = zb.w;
+                if constexpr (KB) { const uint2 zc = *reinterpret_cast<const uint2*>(Z + 8); z[8] = zc.x; z[9] = zc.y; }
+                else { z[8] = z[9] = 0; }
             }
-            const bool pass = filter_pass<NW>(k, sfilt, 32 - kFilterLog2WordsSmem);  // the shared-memory copy always has 2^14 words
-            qtail += (pass && h != 0.0) ? q_adv : 0u;
+            // flag of group j in bit 0 of nz(j)
+            auto nz = [&](int j) -> uint32_t {
+                const uint32_t sh = j == 0 ? P : (P >> (LB * j));
+                if constexpr (KB) {
+                    const uint32_t half = (sh & 32u) ? z[2 * j + 1] : z[2 * j];  // 64-entry mask: bit 5 of the entry picks the word
+                    return __funnelshift_r(half, half, sh);
+                } else {
+                    return __funnelshift_r(z[j], z[j], sh);  // both halves hold the mask: bit 4 of the amount is irrelevant
+                }
+            };
+            uint32_t mask = 0;
+            if (sfilt) {  // warp-uniform
+                const uint32_t* HWB = reinterpret_cast<const uint32_t*>(rec + 64 * NN + HOFF);
+                const uint4 wa = *reinterpret_cast<const uint4*>(HWB), wb = *reinterpret_cast<const uint4*>(HWB + 4);
+                const uint4 ba = *reinterpret_cast<const uint4*>(HWB + 8), bb = *reinterpret_cast<const uint4*>(HWB + 12);
+                const uint32_t hw[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w}, hb[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+                uint32_t word[G];
+#pragma unroll
+                for (int j = 0; j < G; ++j)  // the shared-memory copy always has 2^15 words
+                    word[j] = *reinterpret_cast<const uint32_t*>(sfilt + ((hsw ^ hw[j]) & (kFilterBytes - 4u)));
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    // straight-line bit logic (no lazy evaluation): kill != 0 <=> a filter bit is clear or the LUT entry is exactly 0.0
+                    const uint32_t r = __funnelshift_r(word[j], word[j], hsb ^ hb[j]);
+                    survivor_bit(mask, r, nz(j), 1u << j);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < G; ++j) mask |= (nz(j) & 1u) << j;
+            }
+            // branch-free push: the entry is always written at the tail, the tail only advances when a group survived
+            const uint32_t meta = mask | rec_meta;  // record offset / 16 << 8 | B record << 31 (kept by the record loop)
+            *reinterpret_cast<uint2*>(q0 + (qtail & qwrap)) = make_uint2(P, meta);
+            qtail += mask ? q_adv : 0u;
+            while (__any_sync(0xffffffffu, qtail - qhead > qwrap)) resolve_round(buf);  // a ring is full: the next push needs its tail slot
         };
 
         auto process = [&](const unsigned char* __restrict__ buf, const uint32_t tl_kind, const uint32_t tl_count) {
-            // queue entry of group 0 of the first record: LUT byte offset | (flip-mask offset / 4) << 16; one add per record
-            constexpr uint32_t EB_FIRST = (uint32_t)(64 * NN + UB) | ((uint32_t)(64 * NN / 4) << 16);
-            constexpr uint32_t EB_STEP_A = (uint32_t)REC_A | ((uint32_t)(REC_A / 4) << 16), EB_STEP_B = (uint32_t)REC_B | ((uint32_t)(REC_B / 4) << 16);
-            [[maybe_unused]] uint32_t ebase = EB_FIRST;
             if (tl_kind == kSecA) {
                 const unsigned char* rec = buf;
-                for (uint32_t r = 0; r < tl_count; ++r, rec += REC_A) {
-                    const uint32_t P = parity_word<NN>(rec, nib);
-                    const uint32_t* U = reinterpret_cast<const uint32_t*>(rec + 64 * NN);
-                    const unsigned char* L = rec + 64 * NN + UB;
+                [[maybe_unused]] uint32_t rec_meta = 0;
+                for (uint32_t r = 0; r < tl_count; ++r, rec += REC_A, rec_meta += (REC_A / 16) << 8) {
                     if constexpr (LK == kLookDense) {
+                        const uint32_t P = parity_word<NN>(rec, nib);
+                        const uint32_t* U = reinterpret_cast<const uint32_t*>(rec + 64 * NN);
+                        const unsigned char* L = rec + 64 * NN + UB;
                         const uint32_t* Ux = PSI32 ? U + 8 : U;  // complex64 table: flip masks as byte offsets (u * 8)
                         const uint4 ua = *reinterpret_cast<const uint4*>(Ux), ub = *reinterpret_cast<const uint4*>(Ux + 4);
                         const uint32_t uu[2][4] = {{ua.x, ua.y, ua.z, ua.w}, {ub.x, ub.y, ub.z, ub.w}};
@@ -546,34 +657,17 @@ eloc_sliced_kernel(SlicedView sv, const __grid_constant__ ChunkBounds chunks, ui
                             else emit_batch<NW, SEC, KEYORDER, 4>(h, uu[j0 / 4], s, valid, sec, lv, e_re, e_im);
                         }
                     } else {
-                        // entry = byte offset of the LUT entry | (flip-mask offset / 4) << 16, both relative to the tile buffer
-                        // (tiles of the hash shapes are < 64 KB); ebase follows the record pointer
-                        if (sfilt) {  // warp-uniform
-                            uint4 ua = make_uint4(0, 0, 0, 0), ub = ua;
-                            if constexpr (NW == 1) { ua = *reinterpret_cast<const uint4*>(U); ub = *reinterpret_cast<const uint4*>(U + 4); }
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const uint32_t off = j == 0 ? ((P << 3) & 0x78u) : ((P >> (4 * j - 3)) & 0x78u);
-                                push_filtered(*reinterpret_cast<const double*>(L + j * 128 + off), U, j, ua, ub, ebase + j * (128u + ((uint32_t)NW << 16)) + off);
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const uint32_t off = j == 0 ? ((P << 3) & 0x78u) : ((P >> (4 * j - 3)) & 0x78u);
-                                push(*reinterpret_cast<const double*>(L + j * 128 + off), ebase + j * (128u + ((uint32_t)NW << 16)) + off);
-                            }
-                        }
-                        ebase += EB_STEP_A;
-                        while (__any_sync(0xffffffffu, qtail > q0 + (kQueueCap - 8) * QSTRIDE)) pop_round(buf);
+                        light_record(buf, rec, rec_meta, std::false_type{});
                     }
                 }
             } else if (tl_kind == kSecB) {
                 const unsigned char* rec = buf;
-                for (uint32_t r = 0; r < tl_count; ++r, rec += REC_B) {
-                    const uint32_t P = parity_word<NN>(rec, nib);
-                    const uint32_t* U = reinterpret_cast<const uint32_t*>(rec + 64 * NN);
-                    const unsigned char* L = rec + 64 * NN + UB;
+                [[maybe_unused]] uint32_t rec_meta = 0x80000000u;
+                for (uint32_t r = 0; r < tl_count; ++r, rec += REC_B, rec_meta += (REC_B / 16) << 8) {
                     if constexpr (LK == kLookDense) {
+                        const uint32_t P = parity_word<NN>(rec, nib);
+                        const uint32_t* U = reinterpret_cast<const uint32_t*>(rec + 64 * NN);
+                        const unsigned char* L = rec + 64 * NN + UB;
                         const uint32_t* Ux = PSI32 ? U + 8 : U;
                         const uint4 ua = *reinterpret_cast<const uint4*>(Ux);
                         const uint32_t uu[5] = {ua.x, ua.y, ua.z, ua.w, Ux[4]};
@@ -586,23 +680,7 @@ eloc_sliced_kernel(SlicedView sv, const __grid_constant__ ChunkBounds chunks, ui
                         if constexpr (PSI32) emit_batch32<SEC, 5>(h, uu, a0, base_hi, valid, sec8, e_re, e_im);
                         else emit_batch<NW, SEC, KEYORDER, 5>(h, uu, s, valid, sec, lv, e_re, e_im);
                     } else {
-                        if (sfilt) {  // warp-uniform
-                            uint4 ua = make_uint4(0, 0, 0, 0), ub = ua;
-                            if constexpr (NW == 1) { ua = *reinterpret_cast<const uint4*>(U); ub = *reinterpret_cast<const uint4*>(U + 4); }
-#pragma unroll
-                            for (int j = 0; j < 5; ++j) {
-                                const uint32_t off = j == 0 ? ((P << 3) & 0x1f8u) : ((P >> (6 * j - 3)) & 0x1f8u);
-                                push_filtered(*reinterpret_cast<const double*>(L + j * 512 + off), U, j, ua, ub, ebase + j * (512u + ((uint32_t)NW << 16)) + off);
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 5; ++j) {
-                                const uint32_t off = j == 0 ? ((P << 3) & 0x1f8u) : ((P >> (6 * j - 3)) & 0x1f8u);
-                                push(*reinterpret_cast<const double*>(L + j * 512 + off), ebase + j * (512u + ((uint32_t)NW << 16)) + off);
-                            }
-                        }
-                        ebase += EB_STEP_B;
-                        while (__any_sync(0xffffffffu, qtail > q0 + (kQueueCap - 8) * QSTRIDE)) pop_round(buf);
+                        light_record(buf, rec, rec_meta, std::true_type{});
                     }
                 }
             } else {
@@ -634,8 +712,9 @@ eloc_sliced_kernel(SlicedView sv, const __grid_constant__ ChunkBounds chunks, ui
                         }
                         else {
                             const uint32_t* uu[1] = {hdr + 4};
-                            heavy_lookup<NW, SEC, 1>((h[0] != 0.0 && valid) ? 1 : 0, h, uu, s, sec, lv, sfilt ? sfilt : gfilt,
-                                                     sfilt ? 32 - kFilterLog2WordsSmem : lv.filter_wshift, e_re, e_im);
+                            const uint32_t xw[1] = {hsw ^ hdr[1]}, xb[1] = {hsb ^ hdr[2]};
+                            heavy_lookup<NW, SEC, 1>((h[0] != 0.0 && valid) ? 1 : 0, h, uu, xw, xb, s, sec, lv, sfilt ? sfilt : gfilt,
+                                                     sfilt ? kFilterBytes - 4u : lv.filter_mask, e_re, e_im);
                         }
                     }
                     p += kBlobHeader + (size_t)n_words * REC_C;
@@ -645,23 +724,26 @@ eloc_sliced_kernel(SlicedView sv, const __grid_constant__ ChunkBounds chunks, ui
 
         // (measured alternative: per-buffer "empty" mbarriers released warp by warp + prefetch across state blocks instead of the
         // CTA-wide barrier below — no gain on Li2O, 2 % slower on N2, so the simple form stays)
-        if (threadIdx.x == 0 && tile_lo < tile_hi && !(resident && have_resident)) issue(tile_lo, 0);
+        // a resident tile is read without CTA barriers: before another chunk's tile replaces it, every thread must have left it
+        // (dynamic dealing has barriers at the top of the task loop)
+        if (!have_resident && resident_chunk != -1 && !task_counter) __syncthreads();
+        if (threadIdx.x == 0 && tile_lo < tile_hi && !have_resident) issue(tile_lo, 0);
         for (int t = tile_lo; t < tile_hi; ++t) {
             const int b = resident ? 0 : ((t - tile_lo) & 1);
             if (!resident && threadIdx.x == 0 && t + 1 < tile_hi) issue(t + 1, b ^ 1);
-            if (!(resident && have_resident)) {
+            if (!have_resident) {
                 if (b == 0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1; }
                 else        { mbar_wait(&mbar[1], phase1); phase1 ^= 1; }
             }
-            have_resident = resident;
             const uint32_t tl_kind = sv.tiles[t].kind, tl_count = sv.tiles[t].count;
             process(smem + (size_t)b * buf_bytes, tl_kind, tl_count);
             if constexpr (LK == kLookHash) drain(smem + (size_t)b * buf_bytes);
             if (!resident) __syncthreads();  // every thread is done with buffer b before it is refilled
         }
+        resident_chunk = (resident && tile_lo < tile_hi) ? chunk : -1;
 
         if (valid) {
-            if (KEYORDER || partial) partial[(int64_t)blockIdx.y * M + m] = make_double2(e_re, e_im);
+            if (KEYORDER || partial) partial[(int64_t)chunk * M + m] = make_double2(e_re, e_im);
             else out[m] = finalize_row(make_double2(e_re, e_im), psi, psi_dtype, m);
         }
     }
@@ -681,10 +763,11 @@ __global__ void eloc_finalize_kernel(const double2* __restrict__ partial, int n_
 }
 
 // key-order mode helpers: mark the keys that occur as rows; gather S[key_m] per row, divide and conjugate
-__global__ void mark_keys_kernel(const uint64_t* __restrict__ states, int64_t M, uint32_t* __restrict__ need) {
+__global__ void mark_keys_kernel(const uint64_t* __restrict__ states, int64_t M, uint32_t* __restrict__ need, int64_t n_keys, int* __restrict__ flags) {
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
     const unsigned long long k = states[m];
+    if (k >= (unsigned long long)n_keys) { atomicOr(flags, 1); return; }  // out of range: flagged, never used as an index
     atomicOr(&need[k >> 5], 1u << (k & 31));
 }
 
@@ -694,6 +777,7 @@ __global__ void eloc_rows_finalize_kernel(const double2* __restrict__ partial, i
     const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
     const unsigned long long k = states[m];
+    if (k >= (unsigned long long)n_keys) { out[m] = make_double2(__longlong_as_double(0x7ff8000000000000ll), 0.0); return; }
     double re = 0.0, im = 0.0;
     for (int c = 0; c < n_chunks; ++c) {
         const double2 p = partial[(int64_t)c * n_keys + k];

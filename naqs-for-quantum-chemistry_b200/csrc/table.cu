@@ -1,6 +1,7 @@
 // table.cu — table handle, amplitude lookup construction and the fused E_loc entry points.
 // C ABI documented in include/naqs_eloc.h.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -31,6 +32,19 @@ int ensure_ws(naqs_table* t, size_t bytes) {
 // which IS the reference's sector filter on coupled states (hamiltonian.py:321-328) — applied once per table key here
 // instead of once per (state, group) pair in the fused kernel.  (Sampled states are in-sector by contract; a stray one
 // is ignored exactly as the reference ignores it.)
+// A key with bits at or above n_qubits is not a state index at all (the reference raises IndexError, hilbert.py:607-640 indexes
+// a 2^N LUT with it): it is never used as an address, bit 0 of the table's flag word is raised and naqs_table_check reports it.
+__device__ __forceinline__ bool key_in_range(const uint64_t* __restrict__ key, int words, int n_qubits, int* __restrict__ flags) {
+    bool ok = true;
+    for (int w = 0; w < words; ++w) {
+        const int lo = 64 * w;
+        if (n_qubits <= lo) ok = ok && key[w] == 0ull;
+        else if (n_qubits < lo + 64) ok = ok && (key[w] >> (n_qubits - lo)) == 0ull;
+    }
+    if (!ok && flags) atomicOr(flags, 1);
+    return ok;
+}
+
 __device__ __forceinline__ bool key_in_sector(const uint64_t* __restrict__ key, int words, const Sector& sec) {
     if (!sec.enabled) return true;
     int na = 0, nb = 0;
@@ -64,9 +78,9 @@ __device__ __forceinline__ ulonglong2 cas128(unsigned long long* addr, ulonglong
 }
 
 __global__ void hash_insert_kernel(HashSlot* slots, unsigned long long mask, int shift, const uint64_t* __restrict__ keys, int words,
-                                   const void* __restrict__ psi, int psi_dtype, int64_t n, Sector sec) {
+                                   const void* __restrict__ psi, int psi_dtype, int64_t n, Sector sec, int* __restrict__ flags) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !key_in_sector(keys + i * words, words, sec)) return;
+    if (i >= n || !key_in_range(keys + i * words, words, sec.n_qubits, flags) || !key_in_sector(keys + i * words, words, sec)) return;
     const unsigned long long k0 = keys[i * words], k1 = words > 1 ? keys[i * words + 1] : 0ull;
     const double2 p = load_psi(psi, psi_dtype, i);
     unsigned long long h = hash_slot(k0, k1, shift);
@@ -91,9 +105,9 @@ __global__ void bucket_init_kernel(HashBucket* buckets, int64_t n) {
 }
 
 __global__ void bucket_insert_kernel(HashBucket* buckets, unsigned bmask, int bshift, const uint64_t* __restrict__ keys, int words,
-                                     const void* __restrict__ psi, int psi_dtype, int64_t n, int keep_one, Sector sec) {
+                                     const void* __restrict__ psi, int psi_dtype, int64_t n, int keep_one, Sector sec, int* __restrict__ flags) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !key_in_sector(keys + i * words, words, sec)) return;
+    if (i >= n || !key_in_range(keys + i * words, words, sec.n_qubits, flags) || !key_in_sector(keys + i * words, words, sec)) return;
     const unsigned long long k = keys[i * words];
     const double2 p = load_psi(psi, psi_dtype, i);
     unsigned b = hash32(k, 0ull) >> bshift;
@@ -117,18 +131,48 @@ __global__ void bucket_insert_kernel(HashBucket* buckets, unsigned bmask, int bs
     }
 }
 
-// wide != 0: 128-bit keys — the word comes from the slot hash of both key words (hash_slot), else from the bucket hash
-// small != nullptr: also the 2^14-word companion (same bits, word index from the top 14 hash bits)
-__global__ void filter_build_kernel(uint32_t* filter, int wshift, uint32_t* small, const uint64_t* __restrict__ keys, int words, int wide, int64_t n,
-                                    Sector sec) {
+// Bloom filter over the in-sector table keys from the GF(2)-linear hashes of common.cuh: word = hw & mask (byte offset), bits
+// rotl(kFilterPattern, hb).  small != nullptr: also the 2^15-word companion (same bits, the low 15 bits of the word index).
+__global__ void filter_build_kernel(uint32_t* filter, uint32_t mask, uint32_t* small, const uint64_t* __restrict__ keys, int words, int64_t n, Sector sec,
+                                    int* __restrict__ flags) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !key_in_sector(keys + i * words, words, sec)) return;
-    const unsigned long long k0 = keys[i * words], k1 = wide ? keys[i * words + 1] : 0ull;
-    const uint32_t h = hash32(k0, k1);
-    uint32_t w, b1, b2;
-    filter_word_bits(k0, k1, h, wshift, w, b1, b2);
-    atomicOr(&filter[w], (1u << b1) | (1u << b2));
-    if (small) atomicOr(&small[h >> (32 - kFilterLog2WordsSmem)], (1u << b1) | (1u << b2));
+    if (i >= n || !key_in_range(keys + i * words, words, sec.n_qubits, flags) || !key_in_sector(keys + i * words, words, sec)) return;
+    uint32_t hw, hb;
+    lin_hash_key64(keys + i * words, words, hw, hb);
+    const uint32_t bits = filter_insert_bits(hb);
+    atomicOr(&filter[(hw & mask) >> 2], bits);
+    if (small) atomicOr(&small[(hw & (kFilterBytes - 4u)) >> 2], bits);
+}
+
+// Bank-binned order of a hash-lookup batch: a state's filter BANK is bits 2..6 of its word hash and the bank of a coupled
+// state is bank(s) ^ bank(u) (linear hashes), so a warp whose lane l holds a state of bank l reads 32 different banks for
+// every group.  perm[rank * 32 + bank] = row for the first R states of a bank, later ones go to an overflow region behind
+// the 32 * R regular positions (a skewed batch stays correct, only conflict-prone).  perm is preset to -1, counters to 0.
+template <int NW>
+__global__ void __launch_bounds__(1024) bin_states_kernel(const uint64_t* __restrict__ states, int64_t M, int32_t* __restrict__ perm,
+                                                          int32_t* __restrict__ counters, int64_t R) {
+    __shared__ int cnt[32], base[32];
+    if (threadIdx.x < 32) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t bank = 0;
+    int r = 0;
+    if (m < M) {
+        uint32_t s[NW], hw = 0, hb = 0;
+        load_key<NW>(states, m, s);
+#pragma unroll
+        for (int w = 0; w < NW; ++w) lin_hash_word(s[w], w, hw, hb);
+        bank = (hw >> 2) & 31u;
+        r = atomicAdd(&cnt[bank], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) base[threadIdx.x] = atomicAdd(&counters[threadIdx.x], cnt[threadIdx.x]);
+    __syncthreads();
+    if (m < M) {
+        const int64_t rank = (int64_t)base[bank] + r;
+        const int64_t pos = rank < R ? rank * 32 + bank : 32 * R + atomicAdd(&counters[32], 1);
+        perm[pos] = (int32_t)m;
+    }
 }
 
 __global__ void widen_keys_kernel(const void* __restrict__ in, int itemsize, int64_t n, uint64_t* __restrict__ out) {
@@ -142,15 +186,16 @@ __global__ void narrow_eloc_kernel(const double2* __restrict__ in, int64_t n, fl
     if (i < n) out[i] = make_float2((float)in[i].x, (float)in[i].y);
 }
 
-__global__ void dense_scatter32_kernel(float2* dense, const uint64_t* __restrict__ keys, const float2* __restrict__ psi, int64_t n, Sector sec) {
+__global__ void dense_scatter32_kernel(float2* dense, const uint64_t* __restrict__ keys, const float2* __restrict__ psi, int64_t n, Sector sec,
+                                       int* __restrict__ flags) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && key_in_sector(keys + i, 1, sec)) dense[keys[i]] = psi[i];  // unique keys (caller's guarantee): a plain store
+    if (i < n && key_in_range(keys + i, 1, sec.n_qubits, flags) && key_in_sector(keys + i, 1, sec)) dense[keys[i]] = psi[i];  // unique keys (caller's guarantee): a plain store
 }
 
 __global__ void dense_scatter_kernel(double2* dense, const uint64_t* __restrict__ keys, const void* __restrict__ psi,
-                                     int psi_dtype, int64_t n, int overwrite, Sector sec) {
+                                     int psi_dtype, int64_t n, int overwrite, Sector sec, int* __restrict__ flags) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !key_in_sector(keys + i, 1, sec)) return;
+    if (i >= n || !key_in_range(keys + i, 1, sec.n_qubits, flags) || !key_in_sector(keys + i, 1, sec)) return;
     const double2 p = load_psi(psi, psi_dtype, i);
     if (overwrite) { dense[keys[i]] = p; return; }  // copies of a key carry the same amplitude: keep one
     double* dst = reinterpret_cast<double*>(dense + keys[i]);
@@ -163,13 +208,13 @@ constexpr int kThreads = 256;
 
 // sliced kernel launch shapes: threads per CTA and shared-memory tile capacity (two buffers per CTA)
 // launch shapes [0..2] dense lookup: 1024/512/256 threads, 1/2/4 CTAs per SM (64 registers per thread);
-//               [3..5] hash lookup : same thread counts, smaller tiles: 64 B/thread coupling queue, and a 64 KB Bloom filter
+//               [3..5] hash lookup : same thread counts, smaller tiles: 32-64 B/thread coupling queue, and a 128 KB Bloom filter
 //                                    in the 1-CTA-per-SM shape.  (Measured alternatives: 512 x 1 CTA/SM with 128 registers
 //                                    1.70 ms, 896 threads 1.06 ms, 1024 threads 0.99 ms on Li2O 1e5 — occupancy wins.)
 constexpr int kSlicedThreads[6] = {1024, 512, 256, 1024, 512, 256};
 constexpr int kSlicedCtasPerSm[6] = {1, 2, 4, 1, 2, 4};
 constexpr bool kSlicedFilter[6] = {false, false, false, true, false, false};
-constexpr size_t kSlicedCap[6] = {112640, 55296, 26624, 47104, 36864, 18432};  // [3]: 2 x 46 KB tiles + 64 KB queue + 64 KB filter
+constexpr size_t kSlicedCap[6] = {112640, 55296, 26624, 33792, 36864, 18432};  // [3]: 2 x 33 KB tiles + 32 KB queue + 128 KB filter
 constexpr size_t kSlicedMaxBlob = 16384;
 constexpr size_t kKoMaxBlobWords = 5;  // key-order stream: parity words (30 terms each) of a big group multiplied by psi together
 static_assert(kSlicedCap[3] < 65536 && kSlicedCap[4] < 65536 && kSlicedCap[5] < 65536, "queue entries of the hash shapes hold 16-bit byte offsets into a tile");
@@ -314,6 +359,9 @@ int naqs_table_create(naqs_table_t** out, const uint64_t* h_xy, const uint64_t* 
     t->env_no_dense32 = getenv("NAQS_ELOC_NO_DENSE32") != nullptr;
     t->env_no_filter = getenv("NAQS_ELOC_NO_FILTER") != nullptr;
     t->ko_disabled = getenv("NAQS_ELOC_NO_KO3") != nullptr;
+    t->env_no_bin = getenv("NAQS_ELOC_NO_BIN") != nullptr;
+    t->env_static_tasks = getenv("NAQS_ELOC_STATIC_TASKS") != nullptr;
+    if (const char* e = getenv("NAQS_ELOC_CHUNKS")) t->env_chunks = atoi(e);
 
     int rc = NAQS_OK;
     auto upload = [&](void** dptr, const void* src, size_t bytes) -> int {
@@ -352,6 +400,11 @@ int naqs_table_create(naqs_table_t** out, const uint64_t* h_xy, const uint64_t* 
         }
     }
     if (cudaStreamCreateWithFlags(&t->own_stream, cudaStreamNonBlocking) != cudaSuccess) t->own_stream = nullptr;
+    if (cudaMalloc((void**)&t->d_flags, 4 * sizeof(int)) != cudaSuccess || cudaMemset(t->d_flags, 0, 4 * sizeof(int)) != cudaSuccess) {
+        set_error("naqs_table_create: cudaMalloc of the flag word failed");
+        naqs_table_destroy(t);
+        return NAQS_ERR_ALLOC;
+    }
     *out = t;
     return NAQS_OK;
 }
@@ -365,7 +418,7 @@ int naqs_table_destroy(naqs_table_t* t) {
     if (t->own_stream) cudaStreamDestroy(t->own_stream);
     cudaFree(t->d_tiles); cudaFree(t->d_binom); cudaFree(t->d_stream); cudaFree(t->d_partial);
     for (int c = 0; c < 6; ++c) cudaFree(t->d_stiles[c]);
-    cudaFree(t->d_ko_stream); cudaFree(t->d_ko_ht);
+    cudaFree(t->d_ko_stream); cudaFree(t->d_ko_ht); cudaFree(t->d_flags); cudaFree(t->d_perm);
     delete t;
     return NAQS_OK;
 }
@@ -394,15 +447,15 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
     const int blocks = (int)((n + 255) / 256);
     t->filter_valid = false;
     int rc_f = NAQS_OK;
-    // 2^14 words (the size that fits shared memory; >= 4 bits per key, ~10 % false positives at 2^17 keys) while n <= 2^17;
-    // larger batches get >= 16 bits per key, at most 2^22 words (16 MB, L2-resident) — and, up to 2.5 * 2^17 keys, a 2^14-word
+    // 2^15 words (the size that fits shared memory; >= 4 bits per key) while n <= 2^18;
+    // larger batches get >= 16 bits per key, at most 2^22 words (16 MB, L2-resident) — and, up to 2.5 * 2^18 keys, a 2^15-word
     // companion for shared memory that still rejects more than half of the misses before anything is queued
     auto build_filter = [&](int wide) -> int {
         if (n <= 0 || t->env_no_filter) return NAQS_OK;
         int log2w = kFilterLog2WordsSmem;
         if (4 * n > (32ll << kFilterLog2WordsSmem))
             while (log2w < kFilterLog2WordsMax && (32ll << log2w) < 16 * n) ++log2w;
-        const bool small = log2w > kFilterLog2WordsSmem && 2 * n <= (5ll << 17);
+        const bool small = log2w > kFilterLog2WordsSmem && 2 * n <= (5ll << 18);
         if (t->filter_alloc_log2w < log2w) {
             cudaFree(t->d_filter); t->d_filter = nullptr; t->filter_alloc_log2w = -1;
             NAQS_CUDA(cudaMalloc((void**)&t->d_filter, ((size_t)4 << log2w) + kFilterBytes));
@@ -412,7 +465,8 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
         t->filter_small_valid = small;
         uint32_t* big = t->d_filter + (small ? (1u << kFilterLog2WordsSmem) : 0u);
         NAQS_CUDA(cudaMemsetAsync(t->d_filter, 0, ((size_t)4 << log2w) + (small ? kFilterBytes : 0), stream));
-        filter_build_kernel<<<blocks, 256, 0, stream>>>(big, 32 - log2w, small ? t->d_filter : nullptr, d_keys, t->words, wide, n, t->sector);
+        (void)wide;
+        filter_build_kernel<<<blocks, 256, 0, stream>>>(big, (4u << log2w) - 4u, small ? t->d_filter : nullptr, d_keys, t->words, n, t->sector, t->d_flags);
         NAQS_LAUNCHED();
         t->filter_valid = true;
         return NAQS_OK;
@@ -420,11 +474,6 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
     if (kind == NAQS_LOOKUP_DENSE) {
         NAQS_REQUIRE(t->n_qubits <= 30, NAQS_ERR_ARG, "naqs_lookup_build: dense lookup needs n_qubits <= 30");
         const int64_t entries = 1ll << t->n_qubits;
-        if (t->dense_entries < entries) {
-            cudaFree(t->d_dense); t->d_dense = nullptr; t->dense_entries = 0;
-            NAQS_CUDA(cudaMalloc((void**)&t->d_dense, (size_t)entries * sizeof(double2)));
-            t->dense_entries = entries;
-        }
         // key-order walk + unique complex64 amplitudes: an 8-byte-per-entry table suffices (exact: the kernel widens
         // float -> double, as sparse_math.pyx:33-37 does); otherwise the complex128 table with duplicate summation
         const bool use32 = assume_unique && psi_dtype == NAQS_C64 && t->algo == 0 && n >= entries / 8 && t->n_qubits <= 26 &&
@@ -440,14 +489,19 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
             }
             NAQS_CUDA(cudaMemsetAsync(t->d_dense32, 0, (size_t)entries * sizeof(float2), stream));
             if (n > 0) {
-                dense_scatter32_kernel<<<blocks, 256, 0, stream>>>(t->d_dense32, d_keys, reinterpret_cast<const float2*>(d_psi), n, t->sector);
+                dense_scatter32_kernel<<<blocks, 256, 0, stream>>>(t->d_dense32, d_keys, reinterpret_cast<const float2*>(d_psi), n, t->sector, t->d_flags);
                 NAQS_LAUNCHED();
             }
             t->dense32_valid = true;
         } else {
+            if (t->dense_entries < entries) {  // the 16-byte table is only allocated when it is the one in use
+                cudaFree(t->d_dense); t->d_dense = nullptr; t->dense_entries = 0;
+                NAQS_CUDA(cudaMalloc((void**)&t->d_dense, (size_t)entries * sizeof(double2)));
+                t->dense_entries = entries;
+            }
             NAQS_CUDA(cudaMemsetAsync(t->d_dense, 0, (size_t)entries * sizeof(double2), stream));
             if (n > 0) {
-                dense_scatter_kernel<<<blocks, 256, 0, stream>>>(t->d_dense, d_keys, d_psi, psi_dtype, n, dup_equal ? 1 : 0, t->sector);
+                dense_scatter_kernel<<<blocks, 256, 0, stream>>>(t->d_dense, d_keys, d_psi, psi_dtype, n, dup_equal ? 1 : 0, t->sector, t->d_flags);
                 NAQS_LAUNCHED();
             }
         }
@@ -467,7 +521,7 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
         NAQS_LAUNCHED();
         if (n > 0) {
             const LookupView lv = t->lookup();
-            bucket_insert_kernel<<<blocks, 256, 0, stream>>>(t->d_buckets, lv.bmask, lv.bshift, d_keys, t->words, d_psi, psi_dtype, n, dup_equal ? 1 : 0, t->sector);
+            bucket_insert_kernel<<<blocks, 256, 0, stream>>>(t->d_buckets, lv.bmask, lv.bshift, d_keys, t->words, d_psi, psi_dtype, n, dup_equal ? 1 : 0, t->sector, t->d_flags);
             NAQS_LAUNCHED();
         }
         if ((rc_f = build_filter(0)) != NAQS_OK) return rc_f;
@@ -487,7 +541,7 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
         NAQS_LAUNCHED();
         if (n > 0) {
             hash_insert_kernel<<<blocks, 256, 0, stream>>>(t->d_slots, (unsigned long long)(cap - 1), t->lookup().shift, d_keys, t->words,
-                                                           d_psi, psi_dtype, n, t->sector);
+                                                           d_psi, psi_dtype, n, t->sector, t->d_flags);
             NAQS_LAUNCHED();
         }
         if ((rc_f = build_filter(1)) != NAQS_OK) return rc_f;
@@ -545,9 +599,10 @@ static int launch_sliced_cfg(naqs_table_t* t, const uint64_t* d_states, const vo
     for (int c = 0; c < n_chunks; ++c) max_chunk_tiles = std::max(max_chunk_tiles, cb.lo[c + 1] - cb.lo[c]);
     const size_t cap = kSlicedCap[TL];
     const bool resident = max_chunk_tiles <= 1;
-    const size_t queue_bytes = LK == kLookHash ? (size_t)kQueueCap * 4 * THREADS : 0;
+    const int queue_cap = kSlicedFilter[TL] ? kQueueCapFilter : kQueueCap;
+    const size_t queue_bytes = LK == kLookHash ? (size_t)queue_cap * 8 * THREADS : 0;
     const size_t queue_offset = resident ? cap : 2 * cap;
-    // the Bloom filter is copied to shared memory only in the 1-CTA-per-SM shape (64 KB) and only at its smallest size;
+    // the Bloom filter is copied to shared memory only in the 1-CTA-per-SM shape (128 KB) and only at its smallest size;
     // otherwise the kernel consults it in global memory (L2) before a bucket / slot probe
     const bool use_filter = kSlicedFilter[TL] && t->filter_valid && (t->filter_log2w == kFilterLog2WordsSmem || t->filter_small_valid);
     const size_t filter_offset = queue_offset + queue_bytes;
@@ -571,16 +626,42 @@ static int launch_sliced_cfg(naqs_table_t* t, const uint64_t* d_states, const vo
         if (KEYORDER) {
             need_bits = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(t->d_partial) + (size_t)n_chunks * M * sizeof(double2));
             NAQS_CUDA(cudaMemsetAsync(need_bits, 0, bitmap_bytes, stream));
-            mark_keys_kernel<<<(unsigned)((M_rows + 255) / 256), 256, 0, stream>>>(d_states, M_rows, need_bits);
+            mark_keys_kernel<<<(unsigned)((M_rows + 255) / 256), 256, 0, stream>>>(d_states, M_rows, need_bits, M, t->d_flags);
             NAQS_LAUNCHED();
         }
     }
-    const int64_t n_blocks = (M + THREADS - 1) / THREADS;
+    // hash lookup with the filter in shared memory: walk the rows in bank-binned order (conflict-free filter probes, see
+    // bin_states_kernel); two standard deviations of slack per bank, what does not fit goes to the overflow region
+    BinView bin{nullptr, nullptr, 0};
+    int64_t n_pos = M;
+    if (LK == kLookHash && use_filter && !KEYORDER && !t->env_no_bin && M >= 4096 && M < (1ll << 30)) {
+        const int64_t R = M / 32 + 2 * (int64_t)std::sqrt((double)M / 32.0) + 4;
+        const size_t need = (size_t)(64 + 32 * R + M) * sizeof(int32_t);
+        if (t->perm_bytes < need) {
+            cudaFree(t->d_perm); t->d_perm = nullptr; t->perm_bytes = 0;
+            NAQS_CUDA(cudaMalloc((void**)&t->d_perm, need));
+            t->perm_bytes = need;
+        }
+        NAQS_CUDA(cudaMemsetAsync(t->d_perm, 0, 64 * sizeof(int32_t), stream));
+        NAQS_CUDA(cudaMemsetAsync(t->d_perm + 64, 0xff, (size_t)(32 * R + M) * sizeof(int32_t), stream));
+        bin_states_kernel<NW><<<(unsigned)((M + 1023) / 1024), 1024, 0, stream>>>(d_states, M, t->d_perm + 64, t->d_perm, R);
+        NAQS_LAUNCHED();
+        bin = BinView{t->d_perm + 64, t->d_perm, 32 * R};
+        n_pos = 32 * R + M;  // upper bound for the grid; the kernel reads the true count from the overflow counter
+    }
+    const int64_t n_blocks = (n_pos + THREADS - 1) / THREADS;
     const int slots = sm_count * kSlicedCtasPerSm[TL];
-    dim3 grid((unsigned)std::min<int64_t>(n_blocks, slots), (unsigned)n_chunks);
+    // tasks = (chunk, state block); the hash walk deals them dynamically when a CTA gets more than one (uneven task lengths)
+    const int64_t n_tasks = n_blocks * n_chunks;
+    int* task_counter = nullptr;
+    if (LK == kLookHash && n_tasks > slots && !t->env_static_tasks) {
+        task_counter = t->d_flags + 1;
+        NAQS_CUDA(cudaMemsetAsync(task_counter, 0, sizeof(int), stream));
+    }
+    dim3 grid((unsigned)std::min<int64_t>(n_tasks, slots), 1u);
     SlicedView sv{t->d_stream, (const STile*)t->d_stiles[TL], n_tiles, t->nn};
-    kern<<<grid, THREADS, smem, stream>>>(sv, cb, (uint32_t)cap, (uint32_t)queue_offset, (uint32_t)filter_offset, t->sector, lv, d_states, need_bits, d_psi, psi_dtype,
-                                          M, reinterpret_cast<double2*>(d_eloc), partial);
+    kern<<<grid, THREADS, smem, stream>>>(sv, cb, (uint32_t)cap, (uint32_t)queue_offset, (uint32_t)queue_cap, (uint32_t)filter_offset, t->sector, lv, d_states, need_bits, d_psi, psi_dtype,
+                                          M, bin, n_chunks, task_counter, reinterpret_cast<double2*>(d_eloc), partial);
     NAQS_LAUNCHED();
     if (KEYORDER) {
         eloc_rows_finalize_kernel<<<(unsigned)((M_rows + 255) / 256), 256, 0, stream>>>(partial, n_chunks, M, d_states, d_psi, psi_dtype,
@@ -707,7 +788,7 @@ static int launch_keyorder(naqs_table_t* t, const uint64_t* d_states, const void
     }
     uint32_t* need_bits = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(t->d_partial) + (size_t)p.n_chunks * n_keys * sizeof(double2));
     NAQS_CUDA(cudaMemsetAsync(need_bits, 0, bitmap_bytes, stream));
-    mark_keys_kernel<<<(unsigned)((M_rows + 255) / 256), 256, 0, stream>>>(d_states, M_rows, need_bits);
+    mark_keys_kernel<<<(unsigned)((M_rows + 255) / 256), 256, 0, stream>>>(d_states, M_rows, need_bits, n_keys, t->d_flags);
     NAQS_LAUNCHED();
     const float2* dense32 = t->d_dense32_ext ? t->d_dense32_ext : t->d_dense32;
     int rc;
@@ -741,7 +822,11 @@ static int launch_sliced(naqs_table_t* t, const uint64_t* d_states, const void* 
     int cfg = 2, n_chunks = 1;
     double best_eff = -1.0;
     for (int c = 0; c < 3; ++c) {
-        const int64_t n_blocks = (M + kSlicedThreads[c + tl_off] - 1) / kSlicedThreads[c + tl_off];
+        // the hash walk's 1024-thread shape arranges the rows by filter bank (bin_states_kernel): count the positions it walks
+        const bool binned = tl_off == 3 && kSlicedFilter[c + tl_off] && !t->env_no_bin && M >= 4096 && t->filter_valid &&
+                            (t->filter_log2w == kFilterLog2WordsSmem || t->filter_small_valid);
+        const int64_t M_walk = binned ? M + 64 * (int64_t)std::sqrt((double)M / 32.0) + 128 : M;
+        const int64_t n_blocks = (M_walk + kSlicedThreads[c + tl_off] - 1) / kSlicedThreads[c + tl_off];
         const int64_t slots = (int64_t)sm_count * kSlicedCtasPerSm[c + tl_off];
         const int max_chunks = n_blocks >= slots ? 1 : std::min(t->n_stiles[c + tl_off], 16);
         int ch_best = 1;
@@ -751,9 +836,14 @@ static int launch_sliced(naqs_table_t* t, const uint64_t* d_states, const void* 
             const double eff = n_blocks >= slots ? 1.0 : (double)ctas / (double)(waves * slots) - 0.005 * ch;
             if (eff > eff_best) { eff_best = eff; ch_best = ch; }
         }
+        // hash walk: tasks are dealt dynamically and differ in length, so aim at >= 8 tasks per CTA slot rather than at full waves
+        // (measured on Li2O 1e5: 14 chunks 0.600 ms, 7 chunks 0.635 ms, 3 chunks 0.745 ms)
+        if (tl_off == 3 && n_blocks < slots && !t->env_static_tasks)
+            ch_best = (int)std::min<int64_t>(std::min<int64_t>(kMaxChunks, t->n_stiles[c + tl_off]), std::max<int64_t>(ch_best, (8 * slots + n_blocks - 1) / n_blocks));
         if (eff_best > best_eff + 1e-9) { best_eff = eff_best; cfg = c; n_chunks = ch_best; }
         if (eff_best >= 0.85) { cfg = c; n_chunks = ch_best; break; }
     }
+    if (t->env_chunks > 0) n_chunks = t->env_chunks;  // A/B measurements
     // lookup structures built by this library hold in-sector keys only (key_in_sector above), so a coupled state outside the
     // sector simply misses: the kernel needs its own sector test only for a caller-owned table (naqs_lookup_attach_dense32)
     const bool hash = t->lookup_kind == NAQS_LOOKUP_HASH;
@@ -836,13 +926,15 @@ int naqs_eloc(naqs_table_t* t, const uint64_t* d_states, const void* d_psi, int 
     }
 }
 
-int naqs_dense32_scatter(float* d_table, const uint64_t* d_keys, const void* d_psi, int64_t n, void* stream) {
+int naqs_dense32_scatter(float* d_table, int64_t entries, const uint64_t* d_keys, const void* d_psi, int64_t n, void* stream) {
     NAQS_REQUIRE(n >= 0 && (n == 0 || (d_table && d_keys && d_psi)), NAQS_ERR_ARG, "naqs_dense32_scatter: NULL buffers");
+    NAQS_REQUIRE(entries > 0 && (entries & (entries - 1)) == 0 && entries <= (1ll << 30), NAQS_ERR_ARG, "naqs_dense32_scatter: entries must be a power of two <= 2^30");
     if (n == 0) return NAQS_OK;
     Sector none;  // no table handle here: the fused kernel keeps its own sector test for caller-owned tables
     std::memset(&none, 0, sizeof(none));
+    while ((1ll << none.n_qubits) < entries) ++none.n_qubits;  // keys >= entries are skipped (never used as an address)
     dense_scatter32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2*>(d_table), d_keys,
-                                                                                        reinterpret_cast<const float2*>(d_psi), n, none);
+                                                                                        reinterpret_cast<const float2*>(d_psi), n, none, nullptr);
     NAQS_LAUNCHED();
     return NAQS_OK;
 }
@@ -945,7 +1037,30 @@ int naqs_eloc_host(naqs_table_t* t, const void* h_states, int key_itemsize, cons
     } else {
         NAQS_CUDA(cudaMemcpyAsync(h_eloc, d + o_out, (size_t)M * 16, cudaMemcpyDeviceToHost, st));
     }
+    int h_flags = 0;
+    NAQS_CUDA(cudaMemcpyAsync(&h_flags, t->d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
     NAQS_CUDA(cudaStreamSynchronize(st));
+    if (h_flags & 1) {
+        NAQS_CUDA(cudaMemsetAsync(t->d_flags, 0, sizeof(int), st));
+        set_error("naqs_eloc_host: a state index lies outside [0, 2^n_qubits) (the reference raises IndexError); its row is NaN");
+        return NAQS_ERR_INDEX;
+    }
+    return NAQS_OK;
+}
+
+int naqs_table_check(naqs_table_t* t, void* stream_) {
+    NAQS_REQUIRE(t, NAQS_ERR_ARG, "naqs_table_check: NULL table");
+    DeviceGuard guard(t->device);
+    cudaStream_t st = (cudaStream_t)stream_;
+    int h_flags = 0;
+    NAQS_CUDA(cudaMemcpyAsync(&h_flags, t->d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    NAQS_CUDA(cudaStreamSynchronize(st));
+    if (h_flags & 1) {
+        NAQS_CUDA(cudaMemsetAsync(t->d_flags, 0, sizeof(int), st));
+        set_error("naqs_table_check: a key outside [0, 2^n_qubits) was passed since the last check (the reference raises IndexError); "
+                  "it was ignored as a table key and its row is NaN");
+        return NAQS_ERR_INDEX;
+    }
     return NAQS_OK;
 }
 

@@ -105,7 +105,7 @@ def allreduce_dense_table(table, keys, psi, group=None, out=None):
     out.fill_(INT32_MIN)
     k = keys if keys.dim() == 2 else keys.reshape(-1, 1)
     with torch.cuda.device(table.device):
-        _lib.check(_lib.load().naqs_dense32_scatter(_lib.ptr(out), _lib.ptr(k), _lib.ptr(torch.view_as_real(psi.contiguous())), k.shape[0],
+        _lib.check(_lib.load().naqs_dense32_scatter(_lib.ptr(out), n_entries, _lib.ptr(k), _lib.ptr(torch.view_as_real(psi.contiguous())), k.shape[0],
                                                     _lib.stream_ptr(table.device)), "naqs_dense32_scatter")
     world, _ = _world(group)
     if world > 1:

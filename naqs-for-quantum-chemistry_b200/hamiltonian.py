@@ -106,16 +106,16 @@ class PauliHamiltonianB200:
                   f"(device {self.table.device}).")
 
     # ------------------------------------------------------------------ fused path
-    def local_energy(self, states_idx, psi, ret_numpy=True, assume_unique=True):
+    def local_energy(self, states_idx, psi, ret_numpy=True, assume_unique=True, track=None):
         """E_loc (complex128) of the sampled batch, only couplings inside the batch contribute
         (energy.py:247-248).  Stateless: nothing is cached.  assume_unique=True as in the reference's call
         update_H(states_idx, check_unseen=True, assume_unique=True) (energy.py:245)."""
         on_device = (torch.is_tensor(states_idx) and states_idx.is_cuda) or (torch.is_tensor(psi) and psi.is_cuda)
+        if (self.track_seen if track is None else track) and not self._frozen_H:
+            self._note_seen(states_idx)  # a CUDA batch is kept as a device tensor and only copied if get_H() / save() need it
         if REFERENCE_QUIRKS and self._is_full_sample(states_idx):
             # q1: the reference pairs psi[j] with the j-th sector state in RESTRICTED order here (see REFERENCE_QUIRKS)
             states_idx = self._restricted_full_idxs
-        if self.track_seen and not self._frozen_H and not on_device:
-            self._note_seen(states_idx)
         if ret_numpy and not on_device:
             # host-resident batch (the reference's situation: sampler output is moved to the CPU, nade.py:727-733):
             # one C-ABI call that uploads, computes and downloads (naqs_eloc_host)
@@ -164,19 +164,25 @@ class PauliHamiltonianB200:
             return False
 
     # ------------------------------------------------------------------ reference API
+    def _seen_host(self):
+        return [self.hilbert.to_idx_array(c.cpu() if torch.is_tensor(c) else c).reshape(-1) for c in self._seen_chunks]
+
     def _note_seen(self, states_idx):
-        a = self.hilbert.to_idx_array(states_idx).reshape(-1)
-        self._seen_chunks = list(self._seen_chunks) + [a.copy()]
+        if torch.is_tensor(states_idx) and states_idx.is_cuda:
+            a = states_idx.detach().reshape(-1).clone()
+        else:
+            a = self.hilbert.to_idx_array(states_idx).reshape(-1).copy()
+        self._seen_chunks = list(self._seen_chunks) + [a]
         self._seen_count += len(a)
         if len(self._seen_chunks) > 64 or self._seen_count > 4 * max(len(self._cached_idxs), 1 << 16):
-            u = np.unique(np.concatenate(self._seen_chunks))
+            u = np.unique(np.concatenate(self._seen_host()))
             self._seen_chunks, self._seen_count = [u], len(u)
 
     def _materialize_seen(self):
         """Rows of every state that went through the fused path since the last call -> CSR cache (what the reference's
         update_H side effect at energy.py:245 would have produced)."""
         if self._seen_chunks and not self._frozen_H:
-            seen = np.unique(np.concatenate(self._seen_chunks))
+            seen = np.unique(np.concatenate(self._seen_host()))
             self._seen_chunks, self._seen_count = [], 0
             self.update_H(seen, check_unseen=True, assume_unique=True)
 

@@ -180,6 +180,12 @@ class DeviceTermTable:
                                               _lib.NAQS_C64 if out_dtype == np.dtype(np.complex64) else _lib.NAQS_C128), "naqs_eloc_host")
         return out
 
+    def check(self):
+        """Raise IndexError if a key outside [0, 2^n_qubits) was passed since the last check (the reference raises it at
+        hilbert.py:607-640 / hamiltonian.py:94).  Synchronises the current stream; the host-buffer entry checks itself."""
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().naqs_table_check(self._h, self._stream()), "naqs_table_check")
+
     # ------------------------------------------------------------------ stored rows (CSR / coupled sets)
     def rows(self, states, with_restricted_index=True):
         """Stored couplings of each state (src/optimizer/hamiltonian.py:301-363):

@@ -288,8 +288,14 @@ def main():
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--model-device", default=None)
     ap.add_argument("--record-psi", action="store_true")
+    ap.add_argument("--device-resident", action="store_true", help="b200 backend: install(device_resident=True)")
+    ap.add_argument("--fused-loss", action="store_true", help="b200 backend: install(fused_loss=True)")
     ap.add_argument("--out", required=True)
     a = ap.parse_args()
+    if a.device_resident:
+        os.environ["NAQS_ELOC_DEVICE_RESIDENT"] = "1"
+    if a.fused_loss:
+        os.environ["NAQS_ELOC_FUSED_LOSS"] = "1"
     rec = run_vmc(a.molecule, a.iters, a.seed, a.backend, n_samps=a.n_samps, n_unq_samps_min=a.n_unq_min, n_unq_samps_max=a.n_unq_max,
                   final_solve=not a.no_solve, quiet=not a.verbose, model_device=a.model_device, record_psi=a.record_psi)
     save_record(rec, a.out)
