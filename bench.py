@@ -590,6 +590,7 @@ def main():
     clk_summary = clocks.summary()
     sm_mhz = float(clk_summary.get("sm_mhz") or clk_summary.get("sm_max_mhz") or 1965.0)
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    table_kind = "dense" if wl["N"] <= 22 else "hash"  # NAQS_LOOKUP_AUTO (naqs_lookup_build)
     keyorder_mode = wl["N"] <= 26 and W == 1 and table_kind == "dense" and (T >= (1 << wl["N"]) // 8)
     units = stream_units(np.asarray(wl["xy"]))
     n_units = ((1 << wl["N"]) // 32) if keyorder_mode else (M + 31) // 32

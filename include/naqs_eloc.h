@@ -106,6 +106,34 @@ int naqs_dense32_scatter(float* d_table, int64_t entries, const uint64_t* d_keys
 int naqs_lookup_attach_dense32(naqs_table_t* t, const float* d_table, int64_t n_entries);
 
 /* ------------------------------------------------------------------------------------------
+ * Multi-GPU exchange (the reference is single-process and has nothing to replace here): one process per GPU,
+ * rows sharded, Pauli table replicated.  A communicator wraps an NCCL communicator — created from a unique id the host
+ * distributes (naqs_comm_unique_id on rank 0 -> broadcast -> naqs_comm_init on every rank), or adopted from the caller
+ * (naqs_comm_from_nccl) — and, for key spaces of <= 2^22 states, one CUDA-IPC-mapped region per rank through which the
+ * exchanges run as push kernels over NVLink (csrc/comm.cu). */
+typedef struct naqs_comm naqs_comm_t;
+#define NAQS_COMM_ID_BYTES 128
+#define NAQS_EXCHANGE_GATHER 0x1000 /* force the NCCL all-gather + lookup-build path */
+int naqs_comm_unique_id(void* id128);
+int naqs_comm_init(naqs_comm_t** out, const void* id128, int world_size, int rank, int device);
+int naqs_comm_from_nccl(naqs_comm_t** out, void* nccl_comm, int world_size, int rank, int device);
+int naqs_comm_destroy(naqs_comm_t* c);
+int naqs_comm_info(const naqs_comm_t* c, int* world_size, int* rank);
+/* Make the (key, psi) pairs of ALL ranks the lookup table of `t` (collective; replaces naqs_lookup_build in a sharded step).
+ *   n_qubits <= 22, complex64 psi: every rank stores its pairs straight into the direct-address complex64 table of every
+ *     rank (peer memory), raises a flag there and waits for its peers' flags — one kernel, no reduction (copies of a key on
+ *     several ranks carry the same amplitude by contract), no host synchronisation; the table is then attached like
+ *     naqs_lookup_attach_dense32.  The first call maps the peer regions (synchronous).
+ *   otherwise: NCCL all-gather of the shards padded to max_local (the largest shard, the same value on every rank), then one
+ *     naqs_lookup_build with NAQS_LOOKUP_DUPLICATES_EQUAL; `flags` may carry NAQS_LOOKUP_DENSE / _HASH. */
+int naqs_table_exchange(naqs_table_t* t, naqs_comm_t* c, const uint64_t* d_keys, const void* d_psi, int psi_dtype, int64_t n_local,
+                        int64_t max_local, int flags, void* stream);
+/* In-place all-reduce (sum) of the five statistics sums of naqs_eloc_stats (energy.py:328,372-375).  With a mapped peer
+ * region: one push kernel (each rank writes its sums into a slot of every peer, then adds the slots in rank order — the
+ * result is bitwise identical on every rank); otherwise ncclAllReduce. */
+int naqs_stats_allreduce(naqs_comm_t* c, double* d_sums5, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused local energy — replaces OptimizerBase.calculate_local_energy's body
  * (src/optimizer/energy.py:245-248): update_H + get_H + sparse_dense_mv + "/ psi" + conj.
  *   E_loc[m] = conj( sum_{u} H[s_m, s_m^u] * psi_table(s_m^u) / psi[m] ),

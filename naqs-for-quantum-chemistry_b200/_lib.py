@@ -37,6 +37,13 @@ SIGNATURES = {
     "naqs_lookup_attach_dense32": (_i, [_p, _p, _i64]),
     "naqs_eloc_host": (_i, [_p, _p, _i, _p, _i, _i64, _p, _p, _i64, _i, _p, _i]),
     "naqs_table_check": (_i, [_p, _p]),
+    "naqs_comm_unique_id": (_i, [_p]),
+    "naqs_comm_init": (_i, [C.POINTER(_p), _p, _i, _i, _i]),
+    "naqs_comm_from_nccl": (_i, [C.POINTER(_p), _p, _i, _i, _i]),
+    "naqs_comm_destroy": (_i, [_p]),
+    "naqs_comm_info": (_i, [_p, C.POINTER(_i), C.POINTER(_i)]),
+    "naqs_table_exchange": (_i, [_p, _p, _p, _p, _i, _i64, _i64, _i, _p]),
+    "naqs_stats_allreduce": (_i, [_p, _p, _p]),
     "naqs_rows_count": (_i, [_p, _p, _i64, _p, _p]),
     "naqs_exclusive_scan": (_i, [_p, _p, _i64, _p, _p]),
     "naqs_rows_fill": (_i, [_p, _p, _i64, _p, _p, _p, _p, _p]),

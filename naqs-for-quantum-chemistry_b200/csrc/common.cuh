@@ -280,6 +280,7 @@ struct naqs_table {
     int* d_flags = nullptr;   // [4] device flags (bit 0 of [0]: key out of range), see naqs_table_check
     int32_t* d_perm = nullptr;      // bank-binned order of a hash-lookup batch (bin_states_kernel) + 33 counters in front
     size_t perm_bytes = 0;
+    bool quiet_range_flag = false;  // naqs_table_exchange pads shards with out-of-range keys on purpose
     bool env_no_bin = false, env_static_tasks = false;
     int env_chunks = 0;
 

@@ -446,6 +446,7 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
     NAQS_REQUIRE(kind == NAQS_LOOKUP_DENSE || kind == NAQS_LOOKUP_HASH, NAQS_ERR_ARG, "naqs_lookup_build: bad kind");
     const int blocks = (int)((n + 255) / 256);
     t->filter_valid = false;
+    int* const range_flags = t->quiet_range_flag ? nullptr : t->d_flags;
     int rc_f = NAQS_OK;
     // 2^15 words (the size that fits shared memory; >= 4 bits per key) while n <= 2^18;
     // larger batches get >= 16 bits per key, at most 2^22 words (16 MB, L2-resident) — and, up to 2.5 * 2^18 keys, a 2^15-word
@@ -466,7 +467,7 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
         uint32_t* big = t->d_filter + (small ? (1u << kFilterLog2WordsSmem) : 0u);
         NAQS_CUDA(cudaMemsetAsync(t->d_filter, 0, ((size_t)4 << log2w) + (small ? kFilterBytes : 0), stream));
         (void)wide;
-        filter_build_kernel<<<blocks, 256, 0, stream>>>(big, (4u << log2w) - 4u, small ? t->d_filter : nullptr, d_keys, t->words, n, t->sector, t->d_flags);
+        filter_build_kernel<<<blocks, 256, 0, stream>>>(big, (4u << log2w) - 4u, small ? t->d_filter : nullptr, d_keys, t->words, n, t->sector, range_flags);
         NAQS_LAUNCHED();
         t->filter_valid = true;
         return NAQS_OK;
@@ -489,7 +490,7 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
             }
             NAQS_CUDA(cudaMemsetAsync(t->d_dense32, 0, (size_t)entries * sizeof(float2), stream));
             if (n > 0) {
-                dense_scatter32_kernel<<<blocks, 256, 0, stream>>>(t->d_dense32, d_keys, reinterpret_cast<const float2*>(d_psi), n, t->sector, t->d_flags);
+                dense_scatter32_kernel<<<blocks, 256, 0, stream>>>(t->d_dense32, d_keys, reinterpret_cast<const float2*>(d_psi), n, t->sector, range_flags);
                 NAQS_LAUNCHED();
             }
             t->dense32_valid = true;
@@ -501,7 +502,7 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
             }
             NAQS_CUDA(cudaMemsetAsync(t->d_dense, 0, (size_t)entries * sizeof(double2), stream));
             if (n > 0) {
-                dense_scatter_kernel<<<blocks, 256, 0, stream>>>(t->d_dense, d_keys, d_psi, psi_dtype, n, dup_equal ? 1 : 0, t->sector, t->d_flags);
+                dense_scatter_kernel<<<blocks, 256, 0, stream>>>(t->d_dense, d_keys, d_psi, psi_dtype, n, dup_equal ? 1 : 0, t->sector, range_flags);
                 NAQS_LAUNCHED();
             }
         }
@@ -521,7 +522,7 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
         NAQS_LAUNCHED();
         if (n > 0) {
             const LookupView lv = t->lookup();
-            bucket_insert_kernel<<<blocks, 256, 0, stream>>>(t->d_buckets, lv.bmask, lv.bshift, d_keys, t->words, d_psi, psi_dtype, n, dup_equal ? 1 : 0, t->sector, t->d_flags);
+            bucket_insert_kernel<<<blocks, 256, 0, stream>>>(t->d_buckets, lv.bmask, lv.bshift, d_keys, t->words, d_psi, psi_dtype, n, dup_equal ? 1 : 0, t->sector, range_flags);
             NAQS_LAUNCHED();
         }
         if ((rc_f = build_filter(0)) != NAQS_OK) return rc_f;
@@ -541,7 +542,7 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
         NAQS_LAUNCHED();
         if (n > 0) {
             hash_insert_kernel<<<blocks, 256, 0, stream>>>(t->d_slots, (unsigned long long)(cap - 1), t->lookup().shift, d_keys, t->words,
-                                                           d_psi, psi_dtype, n, t->sector, t->d_flags);
+                                                           d_psi, psi_dtype, n, t->sector, range_flags);
             NAQS_LAUNCHED();
         }
         if ((rc_f = build_filter(1)) != NAQS_OK) return rc_f;

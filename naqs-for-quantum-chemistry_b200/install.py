@@ -19,29 +19,35 @@ from . import hamiltonian_math, hilbert_math, sparse_math
 
 
 def _patch_device_resident(reference_root):
-    """Keep the sampler's output on the GPU: the networks' and wavefunctions' out_device default ("cpu",
-    network/base.py:29,39 and wavefunction.py:27,38-42) becomes the model device, and the two Hilbert helpers the loop
-    applies to the samples accept CUDA tensors: state2idx packs the int8 rows with the device kernel (naqs_state2idx,
-    hilbert.py:573-581), to_idx_array copies to the host only where the reference needs numpy (energy.py:300)."""
+    """Device-resident hand-off from the sampler to the E_loc path: whatever `wavefunction.sample` returns
+    (states, counts, probs, log_psi) is put on the model's device before the loop sees it, and the two Hilbert helpers the
+    loop applies to the samples accept CUDA tensors — state2idx packs the int8 rows with the device kernel (naqs_state2idx,
+    hilbert.py:573-581), to_idx_array copies to the host only where the reference needs numpy (energy.py:300).  From there
+    calculate_local_energy / sgd_step stay on the device.
+    (The reference's NADE cannot simply be given out_device="cuda" — network/base.py:29,39: its sampler builds index tensors
+    on the host, nade.py:585 — so its per-orbital outputs still pass through out_device; that is sampler code, outside this path.)"""
     import functools
 
     import torch
 
     from . import _lib
-    nb = importlib.import_module("src.naqs.network.base")
     wf = importlib.import_module("src.naqs.wavefunction")
     hil = importlib.import_module("src.utils.hilbert")
 
-    def default_out_device(init):
-        @functools.wraps(init)
+    def to_model_device(sample):
+        @functools.wraps(sample)
         def wrapped(self, *a, **k):
-            if k.get("out_device", "cpu") == "cpu" and torch.cuda.is_available() and k.get("device", None) in (None, "cuda"):
-                k["out_device"] = "cuda"
-            return init(self, *a, **k)
+            out = sample(self, *a, **k)
+            dev = getattr(self, "device", "cpu")
+            if not isinstance(out, (list, tuple)) or not torch.cuda.is_available() or str(dev) == "cpu":
+                return out
+            return [o.to(dev, non_blocking=True) if torch.is_tensor(o) else o for o in out]
         return wrapped
 
-    nb.ComplexAutoregressiveMachine_Base.__init__ = default_out_device(nb.ComplexAutoregressiveMachine_Base.__init__)
-    wf._NAQSComplex_Base.__init__ = default_out_device(wf._NAQSComplex_Base.__init__)
+    for name in dir(wf):
+        cls = getattr(wf, name)
+        if isinstance(cls, type) and cls.__module__ == wf.__name__ and "sample" in cls.__dict__ and name != "_NAQSComplex_Base":
+            cls.sample = to_model_device(cls.sample)
 
     def patch_hilbert(cls):
         state2idx_host, to_idx_array_host = cls.state2idx, cls.to_idx_array
@@ -76,8 +82,8 @@ def _patch_device_resident(reference_root):
 def install(reference_root=None, patch_level0=True, patch_level1=True, reference_quirks=None, device_resident=None, fused_loss=None):
     """reference_quirks=True reproduces quirk q1 (hamiltonian.REFERENCE_QUIRKS) for bitwise parity with the reference on
     full-sector batches; None keeps the NAQS_ELOC_REFERENCE_QUIRKS environment setting (default off).
-    device_resident=True (or NAQS_ELOC_DEVICE_RESIDENT=1): the sampler's states / log_psi stay on the GPU and E_loc is computed
-    from them without a host round trip (_patch_device_resident).
+    device_resident=True (or NAQS_ELOC_DEVICE_RESIDENT=1): the sampler's output is handed to the loop on the GPU and state2idx,
+    E_loc and the loss statistics are computed from it without a host round trip (_patch_device_resident; implies fused_loss).
     fused_loss=True (or NAQS_ELOC_FUSED_LOSS=1): OptimizerBase._SGD_step is energy.sgd_step — the loss statistics of
     energy.py:316-329, 367-375 come from one fp64 device kernel and autograd receives a detached weight vector."""
     if os.environ.get("NAQS_ELOC_BACKEND", "b200") == "reference":
@@ -98,12 +104,12 @@ def install(reference_root=None, patch_level0=True, patch_level1=True, reference
         ref_e = importlib.import_module("src.optimizer.energy")
         ref_e.PauliHamiltonian = ref_h.PauliHamiltonian
         ref_e.OptimizerBase.calculate_local_energy = _energy.calculate_local_energy
+        if device_resident is None:
+            device_resident = os.environ.get("NAQS_ELOC_DEVICE_RESIDENT", "0") not in ("", "0")
         if fused_loss is None:
             fused_loss = os.environ.get("NAQS_ELOC_FUSED_LOSS", "0") not in ("", "0")
-        if fused_loss:
+        if fused_loss or device_resident:  # the reference's _SGD_step mixes host and device tensors; the fused step does not
             ref_e.OptimizerBase._SGD_step = _energy.sgd_step
-    if device_resident is None:
-        device_resident = os.environ.get("NAQS_ELOC_DEVICE_RESIDENT", "0") not in ("", "0")
     if device_resident:
         _patch_device_resident(reference_root)
     return True
