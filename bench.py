@@ -464,6 +464,9 @@ def main():
     h_eloc = torch.empty((M, 2), dtype=torch.float64).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     allreduce_table = world > 1 and naqs_b200.distributed.can_allreduce_table(table, d_psi) and not os.environ.get("NAQS_BENCH_ALLGATHER")
+    # multi-GPU exchange: the C-ABI communicator (push kernels over peer memory / NCCL all-gather, csrc/comm.cu) unless
+    # NAQS_BENCH_TORCH_DIST=1 asks for the torch.distributed collectives of round 1
+    comm = naqs_b200.distributed.Comm(dev) if world > 1 and not os.environ.get("NAQS_BENCH_TORCH_DIST") else None
     if world > 1:
         g_states = torch.empty((world * M, W), dtype=torch.int64, device=dev)
         g_psi = torch.empty(world * M, dtype=torch.complex64, device=dev)
@@ -476,7 +479,10 @@ def main():
 
     def step(states, psi, out):
         """One pass of the hot path with device-resident inputs; returns the 5 statistics sums (device)."""
-        if world > 1 and allreduce_table:
+        if comm is not None:
+            # (key, psi) of every rank -> lookup table of this rank, one collective entry (naqs_table_exchange)
+            comm.exchange(table, states, psi, flags=0x1000 if os.environ.get("NAQS_BENCH_ALLGATHER") else 0)
+        elif world > 1 and allreduce_table:
             # small key space: the direct-address table itself is all-reduced (8 * 2^N bytes, independent of the rank count);
             # psi is a function of the state, so copies of a key on several ranks are identical
             naqs_b200.distributed.allreduce_dense_table(table, states, psi, out=dense_tbl)
@@ -491,6 +497,8 @@ def main():
         ev_k0.record()
         table.local_energy(states, psi, out=out, rebuild_lookup=False)
         ev_k1.record()
+        if comm is not None:
+            return comm.allreduce_stats(table.stats(out))
         return naqs_b200.distributed.reduce_stats(table.stats(out))
 
     ev_k0, ev_k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -526,6 +534,36 @@ def main():
     total_ms = float(total_ms.item())
     value = world * M * K * args.steps / (total_ms * 1e-3)
     stats = s5.cpu().numpy()
+
+    # ---- multi-GPU self-check: the all-reduced statistics against ONE rank recomputing the global batch -------------------
+    mgpu_check = None
+    if world > 1:
+        all_k = torch.empty((world * M, W), dtype=torch.int64, device=dev)
+        all_p = torch.empty(world * M, dtype=d_psi.dtype, device=dev)
+        dist.all_gather_into_tensor(all_k, d_states.contiguous())
+        dist.all_gather_into_tensor(torch.view_as_real(all_p), torch.view_as_real(d_psi.contiguous()))
+        if rank == 0:
+            t1 = naqs_b200.DeviceTermTable(wl["xy"], wl["yz"], wl["c"], wl["N"], wl["na"], wl["nb"], device=dev)
+            t1.build_lookup(all_k, all_p, duplicates_equal=True)
+            e1 = t1.local_energy(all_k, all_p, rebuild_lookup=False)
+            s1 = t1.stats(e1).cpu().numpy()
+            mean_m, mean_1 = stats[1] / stats[0], s1[1] / s1[0]
+            var_m, var_1 = stats[3] / stats[0] - mean_m ** 2, s1[3] / s1[0] - mean_1 ** 2
+            mgpu_check = {"rows": int(s1[4]), "mean_rel_diff": float(abs(mean_m - mean_1) / abs(mean_1)),
+                          "var_rel_diff": float(abs(var_m - var_1) / max(abs(var_1), 1e-300)), "n_equal": bool(int(stats[4]) == int(s1[4]))}
+            mgpu_check["ok"] = bool(mgpu_check["n_equal"] and mgpu_check["mean_rel_diff"] <= 1e-12 and mgpu_check["var_rel_diff"] <= 1e-9)
+            # row-level: this rank's shard of the multi-GPU run against the same rows of the single-rank run
+            mgpu_check["shard_max_rel_diff"] = float((d_eloc - e1[:M]).abs().max() / e1[:M].abs().max())
+            mgpu_check["ok"] = bool(mgpu_check["ok"] and mgpu_check["shard_max_rel_diff"] <= 1e-12)
+            del t1, e1
+        del all_k, all_p
+        okt = torch.tensor([1 if (mgpu_check is None or mgpu_check["ok"]) else 0], device=dev)
+        dist.broadcast(okt, 0)
+        if int(okt.item()) != 1:
+            if rank == 0:
+                print(json.dumps({"error": "multi-GPU statistics differ from the single-rank recomputation", "check": mgpu_check}), file=sys.stderr)
+            dist.destroy_process_group()
+            return 1
 
     # ---- end to end through the host-buffer public API -----------------------------------------
     e2e = None
@@ -634,11 +672,14 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": wl["desc"], "states_per_gpu": M, "terms": K, "lookup_keys": T,
-                       "parallelism": f"states sharded x{world}, Pauli table replicated" + ((", NCCL all-reduce (MAX) of the 2^N-entry complex64 amplitude table" if allreduce_table else ", NCCL all-gather of (key, psi)") + " + all-reduce of 5 fp64 sums" if world > 1 else ""),
+                       "parallelism": f"states sharded x{world}, Pauli table replicated" + (
+                           ((", naqs_table_exchange: (key, psi) pushed into every rank's 2^N-entry complex64 table over peer memory" if allreduce_table and not os.environ.get("NAQS_BENCH_ALLGATHER") else ", naqs_table_exchange: NCCL all-gather of (key, psi) + lookup build")
+                            + " + naqs_stats_allreduce of 5 fp64 sums") if comm is not None else
+                           ((", NCCL all-reduce (MAX) of the 2^N-entry complex64 amplitude table" if allreduce_table else ", NCCL all-gather of (key, psi)") + " + all-reduce of 5 fp64 sums" if world > 1 else "")),
                        "l2": "256 MB device memset between timed steps (L2 flush, untimed)", "timing": "CUDA events per step on the launching stream, max over ranks"},
             "clocks": clk_summary, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_pipe": roofline_pipe,
             "cpu_baseline": cpu, "other_configs": extras,
-            "check": {"mean_eloc_re": float(stats[1] / stats[0]), "n": int(stats[4])}}
+            "check": {"mean_eloc_re": float(stats[1] / stats[0]), "n": int(stats[4]), "multi_gpu_vs_single_rank": mgpu_check}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

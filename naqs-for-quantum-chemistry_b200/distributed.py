@@ -122,6 +122,70 @@ def reduce_stats(sums5, group=None):
     return sums5
 
 
+class Comm:
+    """The C-ABI communicator (naqs_comm_t, include/naqs_eloc.h "Multi-GPU exchange"): the table exchange and the statistics
+    all-reduce as push kernels over peer memory (key spaces <= 2^22, complex64 psi) or NCCL all-gather + build.
+    torch.distributed only carries the 128-byte NCCL unique id from rank 0 to the other ranks."""
+
+    def __init__(self, device, group=None):
+        import ctypes as C
+        from . import _lib
+        self.world, self.rank = _world(group)
+        self.device = torch.device(device)
+        self.group = group
+        lib = _lib.load()
+        uid = np.zeros(128, np.uint8)
+        if self.rank == 0:
+            _lib.check(lib.naqs_comm_unique_id(_lib.ptr(uid)), "naqs_comm_unique_id")
+        if self.world > 1:
+            backend = dist.get_backend(group)
+            t = torch.from_numpy(uid).to(self.device if backend == "nccl" else "cpu")
+            dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            uid = t.cpu().numpy()
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.naqs_comm_init(C.byref(self._h), _lib.ptr(np.ascontiguousarray(uid)), self.world, self.rank, self.device.index), "naqs_comm_init")
+
+    def exchange(self, table, keys, psi, max_local=None, flags=0):
+        """(key, psi) shards of all ranks -> lookup table of `table` (naqs_table_exchange).  max_local: the largest shard size
+        (needed by the all-gather path only; default: this shard's size, i.e. equal shards)."""
+        from . import _lib
+        k = _lib.keys_to_device(keys, table.words, table.device)
+        p, code = _lib.psi_to_device(psi, table.device)
+        n = k.shape[0]
+        with torch.cuda.device(table.device):
+            _lib.check(_lib.load().naqs_table_exchange(table._h, self._h, _lib.ptr(k), _lib.ptr(p), code, n, n if max_local is None else int(max_local), flags,
+                                                       _lib.stream_ptr(table.device)), "naqs_table_exchange")
+        table._lookup_built = True
+        return k, p
+
+    def allreduce_stats(self, sums5):
+        from . import _lib
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().naqs_stats_allreduce(self._h, _lib.ptr(sums5), _lib.stream_ptr(self.device)), "naqs_stats_allreduce")
+        return sums5
+
+    def close(self):
+        from . import _lib
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.load().naqs_comm_destroy(self._h)
+            self._h.value = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def sharded_local_energy_comm(table, comm, keys_shard, psi_shard, weights_shard=None, out=None, max_local=None, flags=0):
+    """One sharded step through the C-ABI exchange: naqs_table_exchange -> naqs_eloc on the shard -> naqs_eloc_stats ->
+    naqs_stats_allreduce.  Copies of a key on several ranks must carry the same amplitude (psi is a function of the state)."""
+    k, p = comm.exchange(table, keys_shard, psi_shard, max_local=max_local, flags=flags)
+    eloc = table.local_energy(k, torch.view_as_complex(p), out=out, rebuild_lookup=False)
+    return eloc, comm.allreduce_stats(table.stats(eloc, weights_shard))
+
+
 def sharded_local_energy(table, keys_shard, psi_shard, weights_shard=None, group=None, out=None, equal_sizes=False, gather_out=None,
                          duplicates_equal=False):
     """E_loc of this rank's shard against the batch of ALL ranks, plus the globally reduced statistics.

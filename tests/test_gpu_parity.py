@@ -583,6 +583,26 @@ def _mgpu_worker(rank, world, port, q):
         for other in (eloc3, eloc4):
             diff = float((other - eloc).abs().max() / eloc.abs().max())
             assert diff < 1e-13, diff
+        # the C-ABI exchange (naqs_comm_* / naqs_table_exchange / naqs_stats_allreduce): push kernels over peer memory for this
+        # 20-qubit table, then the NCCL all-gather path with uneven shards (padding must not reach the table)
+        comm = nd.Comm(t.device)
+        t_push = naqs_b200.DeviceTermTable(xy, yz, c, N, na, nb, device=f"cuda:{rank}")
+        sizes = [nd.shard_bounds(len(st), world, r) for r in range(world)]
+        max_local = max(b - a for a, b in sizes)
+        for rep in range(3):  # several epochs: the two peer tables alternate and are cleared in between
+            ps = psi * np.complex64(1.0 + rep)
+            e5, s5 = nd.sharded_local_energy_comm(t_push, comm, st[lo:hi], ps[lo:hi])
+            diff = float((e5 - eloc).abs().max() / eloc.abs().max())
+            assert diff < 1e-13, (rep, diff)
+            st5 = nd.stats_from_sums(s5.cpu().numpy())
+            assert st5["n"] == len(st) and abs(st5["mean"] - stats["mean"]) <= 1e-12 * abs(stats["mean"])
+        from naqs_b200 import _lib as L
+        e6, s6 = nd.sharded_local_energy_comm(table_h, comm, st[lo:hi], psi[lo:hi], max_local=max_local, flags=0x1000 | naqs_b200.table.LOOKUP_HASH)
+        diff = float((e6 - eloc).abs().max() / eloc.abs().max())
+        assert diff < 1e-13, diff
+        table_h.check()  # the out-of-range padding keys of the shorter shard are not reported
+        assert nd.stats_from_sums(s6.cpu().numpy())["n"] == len(st)
+        comm.close()
         q.put((rank, lo, hi, naqs_b200._lib.complex_from_pairs(eloc), stats))
         dist.barrier()
     finally:
