@@ -408,7 +408,50 @@ def measure_extras(naqs_b200, dev, args):
         out["n2_sector_csr_rows"] = rows
     except Exception as e:  # noqa: BLE001
         out["n2_sector_csr_rows"] = {"error": repr(e)}
+    # configs 1 / 4: a VMC iteration of the reference's own loop (experiments/_base._run, flags of batch_train.sh:14) per backend
+    if not args.no_vmc:
+        out["vmc_iteration"] = vmc_iteration_split()
     return out
+
+
+def vmc_iteration_split(molecules=(("LiH", 12, 100000, 10000), ("N2", 12, 1000000, 10000)), timeout=900):
+    """ms per VMC iteration, split sample / state2idx / E_loc / rest (backward + optimizer step), for
+       reference   : the reference's compiled Cython E_loc on the host cores (its own loop, unmodified)
+       b200        : naqs_b200.install() — same loop, E_loc through the C ABI with host buffers
+       b200_device : install(device_resident=True, fused_loss=True) — sampler output handed over on the GPU, fused loss terms
+    The model runs on the GPU in all three (the reference's default).  oracle/ref_vmc.py drives the loop in a subprocess per
+    backend from the staged reference tree (oracle/_ref/tree); the first 2 iterations are dropped as warm-up."""
+    import subprocess
+    import tempfile
+    from oracle import ref_vmc
+    if ref_vmc.tree_root() is None:
+        return {"unavailable": "no reference tree (oracle/_ref/tree is staged by __graft_entry__.build())"}
+    res = {}
+    for mol, iters, n_samps, n_unq_min in molecules:
+        entry = {"iterations": iters - 2, "n_samps": n_samps, "cores": os.cpu_count()}
+        for label, backend, extra in (("reference", "reference", ()), ("b200", "b200", ()), ("b200_device", "b200", ("--device-resident", "--fused-loss"))):
+            with tempfile.TemporaryDirectory() as td:
+                outp = os.path.join(td, "r.npz")
+                cmd = [sys.executable, "-m", "oracle.ref_vmc", "--molecule", mol, "--iters", str(iters), "--seed", "111", "--backend", backend,
+                       "--out", outp, "--no-solve", "--n-samps", str(n_samps), "--n-unq-min", str(n_unq_min), *extra]
+                env = dict(os.environ, NAQS_ELOC_BACKEND=backend)
+                try:
+                    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+                    if r.returncode != 0:
+                        entry[label] = {"error": r.stderr[-400:]}
+                        continue
+                    rec = ref_vmc.load_record(outp)
+                except Exception as e:  # noqa: BLE001
+                    entry[label] = {"error": repr(e)}
+                    continue
+            ms = {k: 1e3 * float(np.mean(rec[k][2:])) if len(rec[k]) > 2 else None for k in ("t_sample", "t_state2idx", "t_eloc", "t_step")}
+            total = sum(v for k, v in ms.items() if v is not None and k != "t_eloc")
+            entry[label] = {"sample_ms": ms["t_sample"], "state2idx_ms": ms["t_state2idx"], "eloc_ms": ms["t_eloc"],
+                            "backward_step_ms": (ms["t_step"] - ms["t_eloc"]) if ms["t_step"] is not None and ms["t_eloc"] is not None else None,
+                            "iteration_ms": total, "unique_states": int(np.mean([len(i) for i in rec["idx"][2:]])) if len(rec["idx"]) > 2 else None,
+                            "last_energy": rec["log_eloc"][-1] if rec["log_eloc"] else None}
+        res[mol] = entry
+    return res
 
 
 # ----------------------------------------------------------------------------------------- B200 arm
@@ -426,6 +469,7 @@ def main():
     ap.add_argument("--strong", action="store_true", help="strong scaling: ONE batch of M states (seed 0) split across the ranks (default: weak, M per rank)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs and the LiH call-latency leg")
+    ap.add_argument("--no-vmc", action="store_true", help="skip the VMC-iteration split of the extras (three subprocess runs per molecule)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -599,7 +643,35 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         host_api = world == 1 and not dedup
-        e2e = {"value": world * M * K * n_e2e / float(dt.item()), "unit": UNIT,
+        serial_value = world * M * K * n_e2e / float(dt.item())
+        e2e_value, pipeline = serial_value, None
+        if host_api:
+            # the same call with TWO batches in flight (naqs_eloc_host_begin / _end, one table handle and one output buffer per
+            # batch): the PCIe copies of one batch overlap the kernel of the other.  Every step still uploads its inputs from
+            # page-locked host memory and downloads its E_loc inside the timed region.
+            table2 = naqs_b200.DeviceTermTable(wl["xy"], wl["yz"], wl["c"], wl["N"], wl["na"], wl["nb"], device=dev)
+            h_eloc32_b = torch.empty(M, dtype=torch.complex64).pin_memory()
+            tabs, outs = (table, table2), (h_eloc32_np, h_eloc32_b.numpy())
+
+            def pipelined(n):
+                for i in range(n):
+                    tabs[i & 1].local_energy_host(h_keys_np, h_psi_np, out=outs[i & 1], assume_unique=True, out_dtype=np.complex64, wait=False)
+                    if i > 0:
+                        tabs[(i - 1) & 1].local_energy_host_wait()
+                tabs[(n - 1) & 1].local_energy_host_wait()
+            pipelined(4)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            pipelined(n_e2e)
+            torch.cuda.synchronize()
+            dt_p = time.perf_counter() - t0
+            assert np.array_equal(outs[0], outs[1])  # both handles computed the same batch
+            e2e_value = M * K * n_e2e / dt_p
+            pipeline = {"batches_in_flight": 2, "serial_value": serial_value,
+                        "note": "value = steady-state rate with two batches in flight (begin/end form of the same call); serial_value = one "
+                                "synchronous call at a time, where upload, kernel and download of a batch cannot overlap (the table is the batch itself)"}
+            del table2
+        e2e = {"value": e2e_value, "unit": UNIT, "pipeline": pipeline,
                "h2d_bytes_per_step": int(M * (h_keys_np.itemsize * (1 if W == 1 else W) + 8)) if host_api else int(M * (8 * W + 8)),
                "d2h_bytes_per_step": int(M * 8) if host_api else int(M * 16), "steps": n_e2e,
                "api": "DeviceTermTable.local_energy_host -> naqs_eloc_host: pinned host state indices (reference index dtype) + complex64 psi in, "

@@ -114,6 +114,8 @@ int naqs_lookup_attach_dense32(naqs_table_t* t, const float* d_table, int64_t n_
 typedef struct naqs_comm naqs_comm_t;
 #define NAQS_COMM_ID_BYTES 128
 #define NAQS_EXCHANGE_GATHER 0x1000 /* force the NCCL all-gather + lookup-build path */
+#define NAQS_EXCHANGE_PUSH 0x2000   /* direct-address table: force the push kernel */
+#define NAQS_EXCHANGE_REDUCE 0x4000 /* direct-address table: force the all-reduce (MAX) of the table */
 int naqs_comm_unique_id(void* id128);
 int naqs_comm_init(naqs_comm_t** out, const void* id128, int world_size, int rank, int device);
 int naqs_comm_from_nccl(naqs_comm_t** out, void* nccl_comm, int world_size, int rank, int device);
@@ -123,7 +125,9 @@ int naqs_comm_info(const naqs_comm_t* c, int* world_size, int* rank);
  *   n_qubits <= 22, complex64 psi: every rank stores its pairs straight into the direct-address complex64 table of every
  *     rank (peer memory), raises a flag there and waits for its peers' flags — one kernel, no reduction (copies of a key on
  *     several ranks carry the same amplitude by contract), no host synchronisation; the table is then attached like
- *     naqs_lookup_attach_dense32.  The first call maps the peer regions (synchronous).
+ *     naqs_lookup_attach_dense32.  The first call maps the peer regions (synchronous).  When the shards are DENSE
+ *     (max_local * (world - 1) > 2^n_qubits / 2: a push would deliver more than the table holds) the table is all-reduced
+ *     instead (fill with -0.0f, scatter, ncclAllReduce MAX on the int32 bit patterns): constant volume, reducible in the switch.
  *   otherwise: NCCL all-gather of the shards padded to max_local (the largest shard, the same value on every rank), then one
  *     naqs_lookup_build with NAQS_LOOKUP_DUPLICATES_EQUAL; `flags` may carry NAQS_LOOKUP_DENSE / _HASH. */
 int naqs_table_exchange(naqs_table_t* t, naqs_comm_t* c, const uint64_t* d_keys, const void* d_psi, int psi_dtype, int64_t n_local,
@@ -185,6 +189,13 @@ int naqs_table_check(naqs_table_t* t, void* stream);
 int naqs_eloc_host(naqs_table_t* t, const void* h_states, int key_itemsize, const void* h_psi, int psi_dtype, int64_t n_states,
                    const void* h_table_keys, const void* h_table_psi, int64_t n_table, int lookup_kind,
                    void* h_eloc, int eloc_dtype);
+/* The same call split in two, for callers that keep several batches in flight (one table handle per batch): _begin enqueues
+ * upload, lookup build, kernel and download on the table's own stream and returns; _end waits for them and reports a key
+ * range error.  With page-locked buffers the copies of one handle overlap the kernel of another (bench.py's pipelined e2e leg).
+ * The host buffers must stay untouched between the two calls. */
+int naqs_eloc_host_begin(naqs_table_t* t, const void* h_states, int key_itemsize, const void* h_psi, int psi_dtype, int64_t n_states,
+                         const void* h_table_keys, const void* h_table_psi, int64_t n_table, int lookup_kind, void* h_eloc, int eloc_dtype);
+int naqs_eloc_host_end(naqs_table_t* t);
 
 /* ------------------------------------------------------------------------------------------
  * Stored Hamiltonian rows (CSR / coupled-set mode) — replaces update_H's row construction

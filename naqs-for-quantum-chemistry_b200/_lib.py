@@ -36,6 +36,8 @@ SIGNATURES = {
     "naqs_dense32_scatter": (_i, [_p, _i64, _p, _p, _i64, _p]),
     "naqs_lookup_attach_dense32": (_i, [_p, _p, _i64]),
     "naqs_eloc_host": (_i, [_p, _p, _i, _p, _i, _i64, _p, _p, _i64, _i, _p, _i]),
+    "naqs_eloc_host_begin": (_i, [_p, _p, _i, _p, _i, _i64, _p, _p, _i64, _i, _p, _i]),
+    "naqs_eloc_host_end": (_i, [_p]),
     "naqs_table_check": (_i, [_p, _p]),
     "naqs_comm_unique_id": (_i, [_p]),
     "naqs_comm_init": (_i, [C.POINTER(_p), _p, _i, _i, _i]),

@@ -3,8 +3,11 @@
 // The reference has no distributed code; the path needs exactly two exchanges per step:
 //   (1) every rank must see the (key, psi) pairs of ALL ranks before it can walk its own rows  -> naqs_table_exchange
 //   (2) the five fp64 statistics sums of the loss are global                                  -> naqs_stats_allreduce
-// Both are written as PUSH kernels over peer memory (CUDA IPC mappings of one region per rank, NVLink / NVSwitch underneath):
-// a rank stores its own contribution straight into every peer's buffer, raises a flag there, and waits for the flags of its
+// Both are written as PUSH kernels over peer memory — except that DENSE shards (a rank's pairs alone would fill a good part
+// of the direct-address table, e.g. 10^6 rows of a 2^20 key space per rank) go through an all-reduce of the table instead: a
+// push delivers every pair to every peer (volume ~ n_local * world), the all-reduce moves the table once whatever the
+// number of ranks and can be reduced inside the NVSwitch.  The statistics always use the push kernel.
+// Push kernels run over CUDA IPC mappings of one region per rank (NVLink / NVSwitch underneath): a rank stores its own contribution straight into every peer's buffer, raises a flag there, and waits for the flags of its
 // peers — no reduction is needed (copies of a key carry the same amplitude by contract, and the sums are added locally in
 // rank order, so the result is bitwise identical on every rank).  One kernel per exchange, no host synchronisation, no NCCL
 // on the data path.  NCCL (loaded at run time from the process, the library torch.distributed uses) does the plumbing:
@@ -69,7 +72,8 @@ constexpr int kMaxRanks = 64;
 // Region layout (identical on every rank except for the table offsets, which each rank aligns in its own address space):
 //   [0, 1024)            flags: int32 [2 kinds][kMaxRanks] — kind 0 table exchange, kind 1 statistics; flag[k][r] = last epoch rank r completed
 //   [1024, 1024 + 8192)  statistics slots: double [2 parities][kMaxRanks][8]
-//   [16384, ...)         two direct-address complex64 tables (2^N entries each), each aligned to its size
+//   [16384, ...)         three direct-address complex64 tables (2^N entries each), each aligned to its size: two alternate
+//                        between the epochs of the push exchange, the third belongs to the all-reduce exchange
 constexpr size_t kFlagsOff = 0, kStatsOff = 1024, kTablesOff = 16384;
 
 struct PeerInfo {
@@ -156,6 +160,22 @@ __global__ void push_stats_kernel(char* const* __restrict__ peer, int world, int
         for (int r = 0; r < world; ++r) acc += slots[r * 8 + t];
         sums5[t] = acc;
     }
+}
+
+// dense shards: the table is pre-filled with -0.0f (bit pattern INT32_MIN: "absent" for a MAX reduction on the int32 patterns
+// and a numeric zero for the kernel), every rank scatters its own pairs, and the tables are all-reduced with MAX — copies of a
+// key on several ranks carry the same amplitude by contract, so MAX simply keeps it.
+__global__ void fill_absent_kernel(int4* __restrict__ table, int64_t n_vec) {
+    const int v = (int)0x80000000u;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) table[i] = make_int4(v, v, v, v);
+}
+__global__ void scatter_table_kernel(float2* __restrict__ table, const uint64_t* __restrict__ keys, const float2* __restrict__ psi, int64_t n, int64_t entries,
+                                     int* __restrict__ err_flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = keys[i];
+    if (k >= (unsigned long long)entries) { if (err_flags) atomicOr(err_flags, 1); return; }
+    table[k] = psi[i];
 }
 
 static int comm_sync_barrier(naqs_comm* c, cudaStream_t st) {  // host-visible barrier through NCCL (setup only)
@@ -294,6 +314,20 @@ int naqs_table_exchange(naqs_table_t* t, naqs_comm_t* c, const uint64_t* d_keys,
         const int64_t entries = 1ll << t->n_qubits;
         int rc = ensure_region(c, entries, st);
         if (rc) return rc;
+        // dense shards -> all-reduce of the table (see the header of this file); sparse shards -> push
+        const bool reduce = c->world > 1 && !(flags & NAQS_EXCHANGE_PUSH) &&
+                            ((flags & NAQS_EXCHANGE_REDUCE) || (double)max_local * (c->world - 1) > 0.5 * (double)entries);
+        if (reduce) {
+            float2* tbl = reinterpret_cast<float2*>(c->region + c->info[(size_t)c->rank].table_off[0] + 2 * (size_t)entries * sizeof(float2));
+            fill_absent_kernel<<<4 * 148, 256, 0, st>>>(reinterpret_cast<int4*>(tbl), entries / 2);
+            NAQS_LAUNCHED();
+            if (n_local > 0) {
+                scatter_table_kernel<<<(unsigned)((n_local + 255) / 256), 256, 0, st>>>(tbl, d_keys, reinterpret_cast<const float2*>(d_psi), n_local, entries, t->d_flags);
+                NAQS_LAUNCHED();
+            }
+            NAQS_NCCL(nccl_api().AllReduce(tbl, tbl, (size_t)entries * 2, ncclInt32, ncclMax, c->nccl, st));
+            return naqs_lookup_attach_dense32(t, reinterpret_cast<const float*>(tbl), entries);
+        }
         const unsigned e = ++c->epoch_table;
         const int cur = (int)(e & 1u), nxt = cur ^ 1;
         // the table of the NEXT step is cleared now, before this rank signals epoch e: a peer only pushes step e + 1 after it has

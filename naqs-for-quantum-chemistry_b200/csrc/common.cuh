@@ -277,6 +277,9 @@ struct naqs_table {
     void* h_pinned = nullptr;
     size_t pinned_bytes = 0;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t last_stream = nullptr;  // stream of the last call that touched the per-table buffers (stream_handover)
+    bool last_stream_valid = false;
+    int* h_flags = nullptr;   // page-locked copy target of d_flags[0] for the host-buffer entry
     int* d_flags = nullptr;   // [4] device flags (bit 0 of [0]: key out of range), see naqs_table_check
     int32_t* d_perm = nullptr;      // bank-binned order of a hash-lookup batch (bin_states_kernel) + 33 counters in front
     size_t perm_bytes = 0;

@@ -27,6 +27,17 @@ int ensure_ws(naqs_table* t, size_t bytes) {
     return NAQS_OK;
 }
 
+// The per-table buffers (lookup structures, partial sums, staging) are reused from call to call.  Calls on ONE stream are
+// ordered by the stream; when the caller switches streams (e.g. the host-buffer entry runs on the table's own stream, the
+// device-tensor entries on the caller's) the previous stream is drained first, so a rebuild can never overtake a kernel
+// that still reads the old table.
+static int stream_handover(naqs_table* t, cudaStream_t stream) {
+    if (t->last_stream_valid && t->last_stream != stream) NAQS_CUDA(cudaStreamSynchronize(t->last_stream));
+    t->last_stream = stream;
+    t->last_stream_valid = true;
+    return NAQS_OK;
+}
+
 // ------------------------------------------------------------------------------------------ lookup build
 // Only keys INSIDE the sector enter a lookup structure: a coupled state s ^ u outside the sector can then never be found,
 // which IS the reference's sector filter on coupled states (hamiltonian.py:321-328) — applied once per table key here
@@ -419,6 +430,7 @@ int naqs_table_destroy(naqs_table_t* t) {
     cudaFree(t->d_tiles); cudaFree(t->d_binom); cudaFree(t->d_stream); cudaFree(t->d_partial);
     for (int c = 0; c < 6; ++c) cudaFree(t->d_stiles[c]);
     cudaFree(t->d_ko_stream); cudaFree(t->d_ko_ht); cudaFree(t->d_flags); cudaFree(t->d_perm);
+    if (t->h_flags) cudaFreeHost(t->h_flags);
     delete t;
     return NAQS_OK;
 }
@@ -437,6 +449,7 @@ int naqs_lookup_build(naqs_table_t* t, const uint64_t* d_keys, const void* d_psi
     NAQS_REQUIRE(psi_dtype == NAQS_C128 || psi_dtype == NAQS_C64, NAQS_ERR_DTYPE, "naqs_lookup_build: psi must be complex64 or complex128");
     DeviceGuard guard(t->device);
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (int rc_s = stream_handover(t, stream)) return rc_s;
     const bool dup_equal = (kind & NAQS_LOOKUP_DUPLICATES_EQUAL) != 0;
     const bool assume_unique = (kind & NAQS_LOOKUP_ASSUME_UNIQUE) != 0 || dup_equal;  // plain stores are exact in both cases
     kind &= 0xff;
@@ -912,6 +925,7 @@ int naqs_eloc(naqs_table_t* t, const uint64_t* d_states, const void* d_psi, int 
     if (M == 0) return NAQS_OK;
     DeviceGuard guard(t->device);
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (int rc_s = stream_handover(t, stream)) return rc_s;
     if (t->algo == 0) {
         switch (t->nn) {
             case 5: return launch_sliced<1, 5>(t, d_states, d_psi, psi_dtype, M, d_eloc, stream);
@@ -963,6 +977,7 @@ int naqs_apply_h(naqs_table_t* t, const uint64_t* d_states, int64_t M, double* d
     // same kernels as naqs_eloc; a NULL psi makes the finalisation write the raw row sums
     DeviceGuard guard(t->device);
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (int rc_s = stream_handover(t, stream)) return rc_s;
     if (t->algo == 0) {
         switch (t->nn) {
             case 5: return launch_sliced<1, 5>(t, d_states, nullptr, NAQS_C128, M, d_out, stream);
@@ -980,6 +995,12 @@ int naqs_apply_h(naqs_table_t* t, const uint64_t* d_states, int64_t M, double* d
 
 int naqs_eloc_host(naqs_table_t* t, const void* h_states, int key_itemsize, const void* h_psi, int psi_dtype, int64_t M,
                    const void* h_tkeys, const void* h_tpsi, int64_t T, int lookup_kind, void* h_eloc, int eloc_dtype) {
+    int rc = naqs_eloc_host_begin(t, h_states, key_itemsize, h_psi, psi_dtype, M, h_tkeys, h_tpsi, T, lookup_kind, h_eloc, eloc_dtype);
+    return rc ? rc : naqs_eloc_host_end(t);
+}
+
+int naqs_eloc_host_begin(naqs_table_t* t, const void* h_states, int key_itemsize, const void* h_psi, int psi_dtype, int64_t M,
+                         const void* h_tkeys, const void* h_tpsi, int64_t T, int lookup_kind, void* h_eloc, int eloc_dtype) {
     NAQS_REQUIRE(t, NAQS_ERR_ARG, "naqs_eloc_host: NULL table");
     NAQS_REQUIRE(M >= 0 && (M == 0 || (h_states && h_psi && h_eloc)), NAQS_ERR_ARG, "naqs_eloc_host: NULL buffers");
     NAQS_REQUIRE(psi_dtype == NAQS_C128 || psi_dtype == NAQS_C64, NAQS_ERR_DTYPE, "naqs_eloc_host: psi must be complex64 or complex128");
@@ -1038,10 +1059,19 @@ int naqs_eloc_host(naqs_table_t* t, const void* h_states, int key_itemsize, cons
     } else {
         NAQS_CUDA(cudaMemcpyAsync(h_eloc, d + o_out, (size_t)M * 16, cudaMemcpyDeviceToHost, st));
     }
-    int h_flags = 0;
-    NAQS_CUDA(cudaMemcpyAsync(&h_flags, t->d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (!t->h_flags) NAQS_CUDA(cudaHostAlloc((void**)&t->h_flags, sizeof(int), cudaHostAllocDefault));
+    NAQS_CUDA(cudaMemcpyAsync(t->h_flags, t->d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    return NAQS_OK;
+}
+
+int naqs_eloc_host_end(naqs_table_t* t) {
+    NAQS_REQUIRE(t, NAQS_ERR_ARG, "naqs_eloc_host_end: NULL table");
+    if (!t->h_flags) return NAQS_OK;  // nothing was begun (or an empty batch)
+    DeviceGuard guard(t->device);
+    cudaStream_t st = t->own_stream;
     NAQS_CUDA(cudaStreamSynchronize(st));
-    if (h_flags & 1) {
+    if (*t->h_flags & 1) {
+        *t->h_flags = 0;
         NAQS_CUDA(cudaMemsetAsync(t->d_flags, 0, sizeof(int), st));
         set_error("naqs_eloc_host: a state index lies outside [0, 2^n_qubits) (the reference raises IndexError); its row is NaN");
         return NAQS_ERR_INDEX;

@@ -147,11 +147,13 @@ class DeviceTermTable:
         return _lib.keys_to_numpy(a, self.words), 8
 
     def local_energy_host(self, states, psi, table_keys=None, table_psi=None, out=None, kind=LOOKUP_AUTO, assume_unique=False,
-                          out_dtype=np.complex128):
+                          out_dtype=np.complex128, wait=True):
         """Host-buffer path (numpy / CPU tensors in, numpy out) through naqs_eloc_host: upload -> lookup build -> fused
         kernel -> download, synchronous.  Keys may be the reference's int16 / int32 state indices or uint64 words; psi
         complex64 / complex128; out_dtype complex128, or complex64 = the float32 pairs the reference returns to torch.
-        Page-locked inputs / `out` (e.g. numpy views of pinned torch tensors) make the copies run at full PCIe rate."""
+        Page-locked inputs / `out` (e.g. numpy views of pinned torch tensors) make the copies run at full PCIe rate.
+        wait=False: only enqueue (naqs_eloc_host_begin) — call `local_energy_host_wait()` before reading `out`; with one table
+        per batch in flight the copies of one batch overlap the kernel of another."""
         k, ksz = self._host_keys(states)
         n = len(k)
         if torch.is_tensor(psi):
@@ -175,10 +177,17 @@ class DeviceTermTable:
                 tk, k, ksz = _lib.keys_to_numpy(tk, self.words), _lib.keys_to_numpy(k, self.words), 8
             tp = np.ascontiguousarray(table_psi).astype(p.dtype).reshape(-1)
             T = len(tk)
-        _lib.check(_lib.load().naqs_eloc_host(self._h, _lib.ptr(k), ksz, _lib.ptr(p), code, n, _lib.ptr(tk), _lib.ptr(tp), T,
-                                              kind | (_lib.LOOKUP_ASSUME_UNIQUE if assume_unique else 0), _lib.ptr(out),
-                                              _lib.NAQS_C64 if out_dtype == np.dtype(np.complex64) else _lib.NAQS_C128), "naqs_eloc_host")
+        fn = _lib.load().naqs_eloc_host if wait else _lib.load().naqs_eloc_host_begin
+        _lib.check(fn(self._h, _lib.ptr(k), ksz, _lib.ptr(p), code, n, _lib.ptr(tk), _lib.ptr(tp), T,
+                      kind | (_lib.LOOKUP_ASSUME_UNIQUE if assume_unique else 0), _lib.ptr(out),
+                      _lib.NAQS_C64 if out_dtype == np.dtype(np.complex64) else _lib.NAQS_C128), "naqs_eloc_host")
+        if not wait:
+            self._host_keepalive = (k, p, tk, tp, out)  # the buffers must outlive the asynchronous copies
         return out
+
+    def local_energy_host_wait(self):
+        _lib.check(_lib.load().naqs_eloc_host_end(self._h), "naqs_eloc_host_end")
+        self._host_keepalive = None
 
     def check(self):
         """Raise IndexError if a key outside [0, 2^n_qubits) was passed since the last check (the reference raises it at
