@@ -19,7 +19,7 @@ def num(x):
 def summarize(path):
     rows = list(csv.reader(open(path)))
     hdr, units = rows[0], rows[1]
-    row = next(r for r in rows[2:] if any("eloc_sliced_kernel" in c for c in r[:12]))
+    row = next(r for r in rows[2:] if any(("eloc_sliced_kernel" in c or "eloc_keyorder_kernel" in c) for c in r[:12]))
     d, u = dict(zip(hdr, row)), dict(zip(hdr, units))
 
     def bytes_of(key):

@@ -31,6 +31,17 @@ extern std::atomic<int64_t> g_launches;
         }                                                                                       \
     } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize sticks to (function, device): raise it once per launch site and device, not per call
+#define NAQS_SMEM_ATTR(kern, bytes, device)                                                     \
+    do {                                                                                        \
+        static int attr_set_[64];                                                               \
+        const int b_ = (int)(bytes);                                                            \
+        if (attr_set_[(device) & 63] < b_) {                                                    \
+            NAQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, b_)); \
+            attr_set_[(device) & 63] = b_;                                                      \
+        }                                                                                       \
+    } while (0)
+
 #define NAQS_REQUIRE(cond, code, msg)                                                           \
     do {                                                                                        \
         if (!(cond)) {                                                                          \

@@ -36,7 +36,7 @@ int launch_rows(naqs_table* t, const uint64_t* d_states, int64_t M, int64_t* d_c
                 uint64_t* d_col_keys, int64_t* d_col_ridx, double* d_vals, cudaStream_t stream) {
     const size_t smem = tile_smem_bytes<NW>(t->tile_cap);
     auto kern = rows_kernel<NW, MODE, kRowThreads>;
-    NAQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NAQS_SMEM_ATTR(kern, smem, t->device);
     const int64_t blocks = (M + kRowThreads - 1) / kRowThreads;
     kern<<<(unsigned)blocks, kRowThreads, smem, stream>>>(t->view(), t->d_tiles, t->n_tiles, t->tile_cap, t->sector, d_states,
                                                          M, t->words, t->d_binom, d_counts, d_indptr, d_col_keys,

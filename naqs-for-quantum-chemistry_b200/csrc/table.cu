@@ -573,7 +573,7 @@ static int launch_eloc(naqs_table_t* t, const uint64_t* d_states, const void* d_
     constexpr int R = 4;
     const size_t smem = tile_smem_bytes<NW>(t->tile_cap);
     auto kern = eloc_direct_kernel<NW, R, kThreads>;
-    NAQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NAQS_SMEM_ATTR(kern, smem, t->device);
     const int64_t per_block = (int64_t)kThreads * R;
     const int64_t blocks = (M + per_block - 1) / per_block;
     kern<<<(unsigned)blocks, kThreads, smem, stream>>>(t->view(), t->d_tiles, t->n_tiles, t->tile_cap,
@@ -622,8 +622,7 @@ static int launch_sliced_cfg(naqs_table_t* t, const uint64_t* d_states, const vo
     const size_t filter_offset = queue_offset + queue_bytes;
     const size_t smem = filter_offset + (use_filter ? kFilterBytes : 0);
     auto kern = eloc_sliced_kernel<NW, NN, THREADS, kSlicedCtasPerSm[TL], LK, SEC, KEYORDER, PSI32>;
-    NAQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(2 * cap + queue_bytes + (kSlicedFilter[TL] ? kFilterBytes : 0))));
+    NAQS_SMEM_ATTR(kern, 2 * cap + queue_bytes + (kSlicedFilter[TL] ? kFilterBytes : 0), t->device);
     LookupView lv = t->lookup();
     lv.filter_in_smem = use_filter ? 1 : 0;
     double2* partial = nullptr;
@@ -776,11 +775,7 @@ template <int SHAPE>
 static int launch_keyorder_shape(naqs_table_t* t, const KoPlan& p, const float2* dense32, const uint32_t* need, int64_t n_tasks, int64_t n_keys,
                                  double2* partial, cudaStream_t stream) {
     auto kern = eloc_keyorder_kernel<kKoThreads[SHAPE], kKoCtasPerSm[SHAPE]>;
-    static bool attr_set[64] = {false};  // per device: the attribute sticks to the function
-    if (!attr_set[t->device & 63]) {
-        NAQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ko_smem_cap(kKoCtasPerSm[SHAPE])));
-        attr_set[t->device & 63] = true;
-    }
+    NAQS_SMEM_ATTR(kern, ko_smem_cap(kKoCtasPerSm[SHAPE]), t->device);
     KoView kv{t->d_ko_stream, t->d_ko_ht, t->ko_n_hi, t->ko_r_total_pad};
     kern<<<dim3((unsigned)p.grid_x, (unsigned)p.n_chunks), kKoThreads[SHAPE], p.smem, stream>>>(kv, p.chunks, p.tw_offset, p.tw_stride, dense32, need,
                                                                                                  n_tasks, n_keys, partial);

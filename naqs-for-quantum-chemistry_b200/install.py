@@ -49,9 +49,10 @@ def _patch_device_resident(reference_root):
         if isinstance(cls, type) and cls.__module__ == wf.__name__ and "sample" in cls.__dict__ and name != "_NAQSComplex_Base":
             cls.sample = to_model_device(cls.sample)
 
-    def patch_hilbert(cls):
-        state2idx_host, to_idx_array_host = cls.state2idx, cls.to_idx_array
+    def patch_state2idx(cls):
+        state2idx_host = cls.state2idx
 
+        @functools.wraps(state2idx_host)
         def state2idx(self, state, use_restricted_idxs=False):
             if not (torch.is_tensor(state) and state.is_cuda):
                 return state2idx_host(self, state, use_restricted_idxs)
@@ -66,17 +67,28 @@ def _patch_device_resident(reference_root):
                 idxs = self.to_idx_tensor(self.full2restricted_idx(idxs.cpu())).to(rows.device)
             return idxs
 
+        cls.state2idx = state2idx
+
+    def patch_to_idx_array(cls):
+        to_idx_array_host = cls.to_idx_array
+
+        @functools.wraps(to_idx_array_host)
         def to_idx_array(self, idx):
             if torch.is_tensor(idx) and idx.is_cuda:
                 idx = idx.cpu()
             return to_idx_array_host(self, idx)
 
-        cls.state2idx, cls.to_idx_array = state2idx, to_idx_array
+        cls.to_idx_array = to_idx_array
 
+    # state2idx is defined per Hilbert flavour (hilbert.py:344, 573, 833; abstract at :51), to_idx_array once in the base (:85)
     for name in dir(hil):
         cls = getattr(hil, name)
-        if isinstance(cls, type) and "state2idx" in cls.__dict__ and "to_idx_array" in cls.__dict__:
-            patch_hilbert(cls)
+        if not isinstance(cls, type) or cls.__module__ != hil.__name__:
+            continue
+        if "state2idx" in cls.__dict__ and not getattr(cls.__dict__["state2idx"], "__isabstractmethod__", False):
+            patch_state2idx(cls)
+        if "to_idx_array" in cls.__dict__:
+            patch_to_idx_array(cls)
 
 
 def install(reference_root=None, patch_level0=True, patch_level1=True, reference_quirks=None, device_resident=None, fused_loss=None):
