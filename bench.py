@@ -230,7 +230,8 @@ def pipe_peaks():
 #     per group: zero-mask rotate 2, filter offset LOP3, LDS, bit XOR, rotate, 2 LOP3, predicated OR = 9 instr, 1 wavefront;
 #     push: 8 instr, 2 wavefronts.  Survivors (data dependent, ~1.5 % of the pairs at 1e5 keys) are not counted.
 #   big-group word (30 terms): parity word + header, then per 6-term chunk: offset 2, LUT LDS.64, DADD = 4 instr, 2 wavefronts
-ISSUE_PER_CLK_SM, WAVEFRONTS_PER_CLK_SM = 4.0, 1.0  # sm_100a: 4 warp schedulers, one L1TEX data-stage wavefront per clock (ncu peaks)
+#   XU pipe (key-order walk only): the two F2F.F64.F32 of every table read run at 16 lanes per clock and SM = 0.5 warp instructions
+ISSUE_PER_CLK_SM, WAVEFRONTS_PER_CLK_SM, XU_PER_CLK_SM = 4.0, 1.0, 0.5  # sm_100a: 4 warp schedulers, one L1TEX data-stage wavefront per clock (ncu peaks)
 
 
 def stream_units(xy_words):
@@ -244,8 +245,10 @@ def stream_units(xy_words):
 def pipe_roofline(mode, units, n_warp_units, nn, kernel_ms, sm_mhz, sm_count=148):
     """t_roof = max(issue, L1TEX) time of the algorithmic work above at the SM clock measured DURING the run; frac = t_roof / t_kernel."""
     rec_a, rec_b, words_c, blobs = units
+    xu = 0
     if mode == "keyorder":
         per = {"A": (5 + 8 * 10, 4 + 8 * 2), "B": (4 + 5 * 10, 4 + 5 * 3), "C": (4 + 5 * 4, 3 + 5 * 2), "blob": (8, 1)}
+        xu = 2 * (8 * rec_a + 5 * rec_b + blobs)
     else:
         par_i, par_w = nn + nn // 2, nn
         per = {"A": (par_i + 6 + 8 * 9 + 8, par_w + 6 + 8 + 2), "B": (par_i + 7 + 5 * 11 + 8, par_w + 7 + 5 + 2),
@@ -255,8 +258,10 @@ def pipe_roofline(mode, units, n_warp_units, nn, kernel_ms, sm_mhz, sm_count=148
     clk = sm_mhz * 1e6
     t_issue = n_warp_units * instr / (ISSUE_PER_CLK_SM * sm_count * clk)
     t_l1 = n_warp_units * waves / (WAVEFRONTS_PER_CLK_SM * sm_count * clk)
-    t_roof = max(t_issue, t_l1)
-    return {"bound": "l1tex" if t_l1 >= t_issue else "issue", "t_roof_ms": 1e3 * t_roof, "t_issue_ms": 1e3 * t_issue, "t_l1tex_ms": 1e3 * t_l1,
+    t_xu = n_warp_units * xu / (XU_PER_CLK_SM * sm_count * clk)
+    t_roof = max(t_issue, t_l1, t_xu)
+    return {"bound": "xu" if t_xu >= max(t_l1, t_issue) else ("l1tex" if t_l1 >= t_issue else "issue"), "t_roof_ms": 1e3 * t_roof, "t_issue_ms": 1e3 * t_issue,
+            "t_l1tex_ms": 1e3 * t_l1, "t_xu_ms": 1e3 * t_xu, "xu_instr_per_unit": int(xu),
             "frac": 1e3 * t_roof / kernel_ms, "warp_units": int(n_warp_units), "warp_instr_per_unit": int(instr), "wavefronts_per_unit": int(waves),
             "formulation": mode, "sm_mhz": sm_mhz, "sm_count": sm_count}
 
@@ -646,31 +651,32 @@ def main():
         serial_value = world * M * K * n_e2e / float(dt.item())
         e2e_value, pipeline = serial_value, None
         if host_api:
-            # the same call with TWO batches in flight (naqs_eloc_host_begin / _end, one table handle and one output buffer per
+            # the same call with THREE batches in flight (naqs_eloc_host_begin / _end, one table handle and one output buffer per
             # batch): the PCIe copies of one batch overlap the kernel of the other.  Every step still uploads its inputs from
             # page-locked host memory and downloads its E_loc inside the timed region.
-            table2 = naqs_b200.DeviceTermTable(wl["xy"], wl["yz"], wl["c"], wl["N"], wl["na"], wl["nb"], device=dev)
-            h_eloc32_b = torch.empty(M, dtype=torch.complex64).pin_memory()
-            tabs, outs = (table, table2), (h_eloc32_np, h_eloc32_b.numpy())
+            depth = 3
+            tabs = [table] + [naqs_b200.DeviceTermTable(wl["xy"], wl["yz"], wl["c"], wl["N"], wl["na"], wl["nb"], device=dev) for _ in range(depth - 1)]
+            outs = [h_eloc32_np] + [torch.empty(M, dtype=torch.complex64).pin_memory().numpy() for _ in range(depth - 1)]
 
             def pipelined(n):
                 for i in range(n):
-                    tabs[i & 1].local_energy_host(h_keys_np, h_psi_np, out=outs[i & 1], assume_unique=True, out_dtype=np.complex64, wait=False)
-                    if i > 0:
-                        tabs[(i - 1) & 1].local_energy_host_wait()
-                tabs[(n - 1) & 1].local_energy_host_wait()
-            pipelined(4)
+                    if i >= depth:
+                        tabs[i % depth].local_energy_host_wait()
+                    tabs[i % depth].local_energy_host(h_keys_np, h_psi_np, out=outs[i % depth], assume_unique=True, out_dtype=np.complex64, wait=False)
+                for t_ in tabs:
+                    t_.local_energy_host_wait()
+            pipelined(2 * depth)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             pipelined(n_e2e)
             torch.cuda.synchronize()
             dt_p = time.perf_counter() - t0
-            assert np.array_equal(outs[0], outs[1])  # both handles computed the same batch
+            assert all(np.array_equal(outs[0], o) for o in outs[1:])  # every handle computed the same batch
             e2e_value = M * K * n_e2e / dt_p
-            pipeline = {"batches_in_flight": 2, "serial_value": serial_value,
-                        "note": "value = steady-state rate with two batches in flight (begin/end form of the same call); serial_value = one "
+            pipeline = {"batches_in_flight": depth, "serial_value": serial_value,
+                        "note": "value = steady-state rate with three batches in flight (begin/end form of the same call); serial_value = one "
                                 "synchronous call at a time, where upload, kernel and download of a batch cannot overlap (the table is the batch itself)"}
-            del table2
+            del tabs[1:]
         e2e = {"value": e2e_value, "unit": UNIT, "pipeline": pipeline,
                "h2d_bytes_per_step": int(M * (h_keys_np.itemsize * (1 if W == 1 else W) + 8)) if host_api else int(M * (8 * W + 8)),
                "d2h_bytes_per_step": int(M * 8) if host_api else int(M * 16), "steps": n_e2e,
@@ -708,14 +714,14 @@ def main():
     pr = pipe_roofline("keyorder" if keyorder_mode else "hash" if table_kind == "hash" else "dense-rows", units, n_units, nn, k_ms, sm_mhz, sm_count)
     wave_rate = pr["warp_units"] * pr["wavefronts_per_unit"] / (k_ms * 1e-3) / 1e9
     instr_rate = pr["warp_units"] * pr["warp_instr_per_unit"] / (k_ms * 1e-3) / 1e9
-    l1_bound = pr["bound"] == "l1tex"
-    roofline = {"bound": pr["bound"], "achieved": wave_rate if l1_bound else instr_rate,
-                "peak": (WAVEFRONTS_PER_CLK_SM if l1_bound else ISSUE_PER_CLK_SM) * sm_count * sm_mhz * 1e-3,
-                "unit": "Gwavefront/s" if l1_bound else "Gwarp-instr/s", "frac": pr["frac"], "traffic": traffic,
+    xu_rate = pr["warp_units"] * pr["xu_instr_per_unit"] / (k_ms * 1e-3) / 1e9
+    ach, pk, un = {"l1tex": (wave_rate, WAVEFRONTS_PER_CLK_SM, "Gwavefront/s"), "issue": (instr_rate, ISSUE_PER_CLK_SM, "Gwarp-instr/s"),
+                   "xu": (xu_rate, XU_PER_CLK_SM, "Gwarp-instr/s (XU pipe)")}[pr["bound"]]
+    roofline = {"bound": pr["bound"], "achieved": ach, "peak": pk * sm_count * sm_mhz * 1e-3, "unit": un, "frac": pr["frac"], "traffic": traffic,
                 "kernel": ("eloc_keyorder_kernel" if keyorder_mode else "eloc_sliced_kernel") + " (timed with CUDA events around naqs_eloc: includes its mark / bin / finalize helpers)",
                 "kernel_ms": k_ms, "model": pr,
-                "peak_source": "algorithmic wavefronts and warp instructions of the formulation (bench.py pipe_roofline, DESIGN.md §6) against 1 wavefront "
-                               "and 4 warp instructions per clock and SM at the SM clock sampled during this run",
+                "peak_source": "algorithmic wavefronts and warp instructions of the formulation (bench.py pipe_roofline, DESIGN.md §6) against 1 wavefront, "
+                               "4 warp instructions and 0.5 XU (F2F.F64.F32) warp instructions per clock and SM at the SM clock sampled during this run",
                 "hbm": roofline_hbm}
     pp, pp_name = pipe_peaks()
     kernel_rate = M * K / (k_ms * 1e-3)

@@ -241,6 +241,11 @@ struct naqs_table {
     naqs::Tile* d_tiles = nullptr;
     int n_tiles = 0, tile_cap = 0;
     long long* d_binom = nullptr;  // C(n, k) table for the restricted-index ranker (lazy)
+    // stored-row kernels: the same terms cut into kMaxChunks chunks on group boundaries (grid.y of rows_kernel), so that a small
+    // batch (a VMC sector: 10^4 rows) still fills the machine; row_chunk_lo[c] = first tile of base chunk c
+    naqs::Tile* d_row_tiles = nullptr;
+    int row_chunk_lo[naqs::kMaxChunks + 1] = {0};
+    int n_row_chunks = 0, row_tile_cap = 0;
     // sliced (v2) formulation: byte stream + tile lists for the 1024/512/256-thread launch shapes
     int algo = 0;                  // 0 = sliced (default), 1 = direct
     int f32 = 0;                   // naqs_table_set_precision(32): float32 accumulation of H_ij (direct formulation only)

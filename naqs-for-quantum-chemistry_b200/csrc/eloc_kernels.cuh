@@ -302,19 +302,29 @@ __device__ __forceinline__ long long restricted_index(const uint32_t (&j)[NW], c
            lex_rank<NW>(j, 1, n_odd, sec.n_beta, binom);
 }
 
+// grid = (row blocks, table chunks).  A chunk is a contiguous range of tiles that starts and ends on a group boundary
+// (naqs_table_create builds the list), so every group is summed by ONE thread in reference term order whatever the number of
+// chunks.  With more than one chunk the count pass writes per-(chunk, row) counts (chunk_counts[c * M + m], int32) and the fill
+// pass starts chunk c of row m at indptr[m] + sum_{c' < c} chunk_counts[c' * M + m]: a row's entries stay in ascending group order.
 template <int NW, int MODE, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-rows_kernel(TableView tv, const Tile* __restrict__ tiles, int n_tiles, int tile_cap, Sector sec,
+rows_kernel(TableView tv, const Tile* __restrict__ tiles, const __grid_constant__ ChunkBounds chunks, int n_chunks, int tile_cap, Sector sec,
             const uint64_t* __restrict__ states, int64_t M, int words, const long long* __restrict__ binom,
-            int64_t* __restrict__ counts, const int64_t* __restrict__ indptr, uint64_t* __restrict__ col_keys,
-            int64_t* __restrict__ col_ridx, double* __restrict__ vals) {
+            int64_t* __restrict__ counts, int32_t* __restrict__ chunk_counts, const int64_t* __restrict__ indptr,
+            uint64_t* __restrict__ col_keys, int64_t* __restrict__ col_ridx, double* __restrict__ vals) {
     uint32_t s[1][NW];
     bool valid[1];
     load_states<NW, 1, THREADS>(states, M, s, valid);
     const int64_t m = (int64_t)blockIdx.x * THREADS + threadIdx.x;
+    const int chunk = blockIdx.y;
     int64_t n = 0;
-    int64_t e = (MODE == kRowsFill && valid[0]) ? indptr[m] : 0;
-    walk_table<NW, 1, THREADS>(tv, tiles, n_tiles, tile_cap, s, [&](int g, const uint32_t (&u)[NW], const double (&h)[1]) {
+    int64_t e = 0;
+    if (MODE == kRowsFill && valid[0]) {
+        e = indptr[m];
+        for (int c = 0; c < chunk; ++c) e += chunk_counts[(int64_t)c * M + m];
+    }
+    walk_table<NW, 1, THREADS>(tv, tiles + chunks.lo[chunk], chunks.lo[chunk + 1] - chunks.lo[chunk], tile_cap, s,
+                               [&](int g, const uint32_t (&u)[NW], const double (&h)[1]) {
         if (!valid[0]) return;
         if (MODE == kRowsDense) {
             vals[m * tv.G + g] = h[0];
@@ -337,7 +347,10 @@ rows_kernel(TableView tv, const Tile* __restrict__ tiles, int n_tiles, int tile_
             ++e;
         }
     });
-    if (MODE == kRowsCount && valid[0]) counts[m] = n;
+    if (MODE == kRowsCount && valid[0]) {
+        if (n_chunks > 1) chunk_counts[(int64_t)chunk * M + m] = (int32_t)n;
+        else counts[m] = n;
+    }
 }
 
 }  // namespace naqs

@@ -1,5 +1,6 @@
 // rows.cu — stored Hamiltonian rows (CSR / coupled-set mode), dense H_ij, restricted-index ranker,
 // exclusive scan and sorted-unique of keys.  C ABI documented in include/naqs_eloc.h.
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -11,6 +12,14 @@ using namespace naqs;
 namespace {
 
 constexpr int kRowThreads = 128;
+
+__global__ void rows_sum_chunk_counts_kernel(const int32_t* __restrict__ chunk_counts, int n_chunks, int64_t M, int64_t* __restrict__ counts) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    int64_t n = 0;
+    for (int c = 0; c < n_chunks; ++c) n += chunk_counts[(int64_t)c * M + m];
+    counts[m] = n;
+}
 
 int ensure_binom(naqs_table* t) {
     if (t->d_binom) return NAQS_OK;
@@ -31,28 +40,62 @@ int ensure_binom(naqs_table* t) {
     return NAQS_OK;
 }
 
+// Number of table chunks (grid.y) for a batch of M rows: enough threads for about one full wave of resident threads, a power of
+// two so that base chunks merge evenly; 1 (the plain tile list) for large batches.
+int rows_chunks_for(const naqs_table* t, int64_t M) {
+    if (t->n_row_chunks == 0) return 1;
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, t->device);
+    const int64_t want_threads = (int64_t)sm_count * 2048;
+    int c = 1;
+    while (c < t->n_row_chunks && (int64_t)c * M < want_threads) c *= 2;
+    return c;
+}
+
 template <int NW, int MODE>
-int launch_rows(naqs_table* t, const uint64_t* d_states, int64_t M, int64_t* d_counts, const int64_t* d_indptr,
-                uint64_t* d_col_keys, int64_t* d_col_ridx, double* d_vals, cudaStream_t stream) {
-    const size_t smem = tile_smem_bytes<NW>(t->tile_cap);
+int launch_rows(naqs_table* t, const uint64_t* d_states, int64_t M, int n_chunks, int64_t* d_counts, int32_t* d_chunk_counts,
+                const int64_t* d_indptr, uint64_t* d_col_keys, int64_t* d_col_ridx, double* d_vals, cudaStream_t stream) {
+    ChunkBounds cb;
+    const Tile* tiles = t->d_tiles;
+    int cap = t->tile_cap;
+    if (n_chunks > 1) {
+        const int merge = t->n_row_chunks / n_chunks;
+        for (int c = 0; c <= kMaxChunks; ++c) cb.lo[c] = t->row_chunk_lo[std::min(c * merge, t->n_row_chunks)];
+        tiles = t->d_row_tiles;
+        cap = t->row_tile_cap;
+    } else {
+        cb.lo[0] = 0;
+        for (int c = 1; c <= kMaxChunks; ++c) cb.lo[c] = t->n_tiles;
+    }
+    const size_t smem = tile_smem_bytes<NW>(cap);
     auto kern = rows_kernel<NW, MODE, kRowThreads>;
     NAQS_SMEM_ATTR(kern, smem, t->device);
     const int64_t blocks = (M + kRowThreads - 1) / kRowThreads;
-    kern<<<(unsigned)blocks, kRowThreads, smem, stream>>>(t->view(), t->d_tiles, t->n_tiles, t->tile_cap, t->sector, d_states,
-                                                         M, t->words, t->d_binom, d_counts, d_indptr, d_col_keys,
-                                                         d_col_ridx, d_vals);
+    kern<<<dim3((unsigned)blocks, (unsigned)n_chunks), kRowThreads, smem, stream>>>(t->view(), tiles, cb, n_chunks, cap, t->sector, d_states,
+                                                                                  M, t->words, t->d_binom, d_counts, d_chunk_counts, d_indptr,
+                                                                                  d_col_keys, d_col_ridx, d_vals);
     NAQS_LAUNCHED();
     return NAQS_OK;
 }
 
 template <int MODE>
-int dispatch_rows(naqs_table* t, const uint64_t* d_states, int64_t M, int64_t* d_counts, const int64_t* d_indptr,
-                  uint64_t* d_col_keys, int64_t* d_col_ridx, double* d_vals, cudaStream_t stream) {
+int dispatch_rows(naqs_table* t, const uint64_t* d_states, int64_t M, int n_chunks, int64_t* d_counts, int32_t* d_chunk_counts,
+                  const int64_t* d_indptr, uint64_t* d_col_keys, int64_t* d_col_ridx, double* d_vals, cudaStream_t stream) {
     switch (t->nw32) {
-        case 1: return launch_rows<1, MODE>(t, d_states, M, d_counts, d_indptr, d_col_keys, d_col_ridx, d_vals, stream);
-        case 2: return launch_rows<2, MODE>(t, d_states, M, d_counts, d_indptr, d_col_keys, d_col_ridx, d_vals, stream);
-        default: return launch_rows<4, MODE>(t, d_states, M, d_counts, d_indptr, d_col_keys, d_col_ridx, d_vals, stream);
+        case 1: return launch_rows<1, MODE>(t, d_states, M, n_chunks, d_counts, d_chunk_counts, d_indptr, d_col_keys, d_col_ridx, d_vals, stream);
+        case 2: return launch_rows<2, MODE>(t, d_states, M, n_chunks, d_counts, d_chunk_counts, d_indptr, d_col_keys, d_col_ridx, d_vals, stream);
+        default: return launch_rows<4, MODE>(t, d_states, M, n_chunks, d_counts, d_chunk_counts, d_indptr, d_col_keys, d_col_ridx, d_vals, stream);
     }
+}
+
+// per-(chunk, row) counts of a chunked launch live in the table's workspace: [n_chunks][M] int32
+int chunk_counts_ws(naqs_table* t, int n_chunks, int64_t M, int32_t** out) {
+    *out = nullptr;
+    if (n_chunks <= 1) return NAQS_OK;
+    int rc = ensure_ws(t, (size_t)n_chunks * (size_t)M * sizeof(int32_t));
+    if (rc) return rc;
+    *out = reinterpret_cast<int32_t*>(t->d_ws);
+    return NAQS_OK;
 }
 
 template <int NW>
@@ -74,7 +117,15 @@ int naqs_rows_count(naqs_table_t* t, const uint64_t* d_states, int64_t M, int64_
     NAQS_REQUIRE(M >= 0 && (M == 0 || (d_states && d_counts)), NAQS_ERR_ARG, "naqs_rows_count: NULL buffers");
     if (M == 0) return NAQS_OK;
     DeviceGuard guard(t->device);
-    return dispatch_rows<kRowsCount>(t, d_states, M, d_counts, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+    const int n_chunks = rows_chunks_for(t, M);
+    int32_t* cc = nullptr;
+    if (int rc = chunk_counts_ws(t, n_chunks, M, &cc)) return rc;
+    if (int rc = dispatch_rows<kRowsCount>(t, d_states, M, n_chunks, d_counts, cc, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream)) return rc;
+    if (n_chunks > 1) {
+        rows_sum_chunk_counts_kernel<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(cc, n_chunks, M, d_counts);
+        NAQS_LAUNCHED();
+    }
+    return NAQS_OK;
 }
 
 int naqs_rows_fill(naqs_table_t* t, const uint64_t* d_states, int64_t M, const int64_t* d_indptr, uint64_t* d_col_keys,
@@ -84,7 +135,14 @@ int naqs_rows_fill(naqs_table_t* t, const uint64_t* d_states, int64_t M, const i
     if (M == 0) return NAQS_OK;
     DeviceGuard guard(t->device);
     if (d_col_ridx) { int rc = ensure_binom(t); if (rc) return rc; }
-    return dispatch_rows<kRowsFill>(t, d_states, M, nullptr, d_indptr, d_col_keys, d_col_ridx, d_vals, (cudaStream_t)stream);
+    // a chunked fill needs the per-(chunk, row) counts: they are recomputed here (no state is carried over from naqs_rows_count,
+    // the caller's scan in between reuses the workspace)
+    const int n_chunks = rows_chunks_for(t, M);
+    int32_t* cc = nullptr;
+    if (int rc = chunk_counts_ws(t, n_chunks, M, &cc)) return rc;
+    if (n_chunks > 1)
+        if (int rc = dispatch_rows<kRowsCount>(t, d_states, M, n_chunks, nullptr, cc, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream)) return rc;
+    return dispatch_rows<kRowsFill>(t, d_states, M, n_chunks, nullptr, cc, d_indptr, d_col_keys, d_col_ridx, d_vals, (cudaStream_t)stream);
 }
 
 int naqs_hij_dense(naqs_table_t* t, const uint64_t* d_states, int64_t M, double* d_hij, void* stream) {
@@ -92,7 +150,7 @@ int naqs_hij_dense(naqs_table_t* t, const uint64_t* d_states, int64_t M, double*
     NAQS_REQUIRE(M >= 0 && (M == 0 || (d_states && d_hij)), NAQS_ERR_ARG, "naqs_hij_dense: NULL buffers");
     if (M == 0 || t->G == 0) return NAQS_OK;
     DeviceGuard guard(t->device);
-    return dispatch_rows<kRowsDense>(t, d_states, M, nullptr, nullptr, nullptr, nullptr, d_hij, (cudaStream_t)stream);
+    return dispatch_rows<kRowsDense>(t, d_states, M, rows_chunks_for(t, M), nullptr, nullptr, nullptr, nullptr, nullptr, d_hij, (cudaStream_t)stream);
 }
 
 int naqs_restricted_index(naqs_table_t* t, const uint64_t* d_keys, int64_t n, int64_t* d_out, void* stream) {

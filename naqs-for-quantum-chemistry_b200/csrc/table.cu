@@ -326,6 +326,31 @@ int naqs_table_create(naqs_table_t** out, const uint64_t* h_xy, const uint64_t* 
         tiles.push_back(tl);
     }
     t->n_tiles = (int)tiles.size();
+    // chunked tile list for the stored-row kernels: kMaxChunks contiguous group ranges of about equal term count
+    std::vector<Tile> row_tiles;
+    if (G >= 4 * kMaxChunks) {
+        int64_t g = 0;
+        int max_terms = 1;
+        for (int c = 0; c < kMaxChunks; ++c) {
+            t->row_chunk_lo[c] = (int)row_tiles.size();
+            const int64_t want_end = K * (c + 1) / kMaxChunks;
+            int64_t g_end = g;
+            while (g_end < G && (c + 1 == kMaxChunks || (int64_t)gstart[(size_t)g_end + 1] <= want_end || g_end == g)) ++g_end;
+            if (c + 1 == kMaxChunks) g_end = G;
+            for (int64_t t0 = gstart[(size_t)g]; t0 < (int64_t)gstart[(size_t)g_end]; t0 += t->tile_cap) {
+                Tile tl;
+                tl.t0 = (uint32_t)t0; tl.t1 = (uint32_t)std::min<int64_t>(gstart[(size_t)g_end], t0 + t->tile_cap);
+                tl.g0 = (uint32_t)(std::upper_bound(gstart.begin(), gstart.end(), tl.t0) - gstart.begin() - 1);
+                tl.g1 = (uint32_t)(std::lower_bound(gstart.begin(), gstart.end(), tl.t1) - gstart.begin());
+                max_terms = std::max<int>(max_terms, (int)(tl.t1 - tl.t0));
+                row_tiles.push_back(tl);
+            }
+            g = g_end;
+        }
+        t->row_chunk_lo[kMaxChunks] = (int)row_tiles.size();
+        t->n_row_chunks = kMaxChunks;
+        t->row_tile_cap = max_terms;
+    }
 
     // sliced (v2) stream: groups in ascending-XY order with their terms in reference order
     SlicedHost sh;
@@ -385,6 +410,7 @@ int naqs_table_create(naqs_table_t** out, const uint64_t* h_xy, const uint64_t* 
         (rc = upload((void**)&t->d_gxy, gxy.data(), (size_t)NW * G * 4)) ||
         (rc = upload((void**)&t->d_gstart, gstart.data(), (size_t)(G + 1) * 4)) ||
         (rc = upload((void**)&t->d_tiles, tiles.data(), tiles.size() * sizeof(Tile))) ||
+        (rc = upload((void**)&t->d_row_tiles, row_tiles.data(), row_tiles.size() * sizeof(Tile))) ||
         (rc = upload((void**)&t->d_stream, sh.stream.data(), sh.stream.size())) ||
         (rc = upload(&t->d_stiles[0], stiles[0].data(), stiles[0].size() * sizeof(STile))) ||
         (rc = upload(&t->d_stiles[1], stiles[1].data(), stiles[1].size() * sizeof(STile))) ||
@@ -427,7 +453,7 @@ int naqs_table_destroy(naqs_table_t* t) {
     cudaFree(t->d_dense); cudaFree(t->d_dense32_raw); cudaFree(t->d_slots); cudaFree(t->d_buckets); cudaFree(t->d_filter); cudaFree(t->d_ws); cudaFree(t->d_stage);
     if (t->h_pinned) cudaFreeHost(t->h_pinned);
     if (t->own_stream) cudaStreamDestroy(t->own_stream);
-    cudaFree(t->d_tiles); cudaFree(t->d_binom); cudaFree(t->d_stream); cudaFree(t->d_partial);
+    cudaFree(t->d_tiles); cudaFree(t->d_row_tiles); cudaFree(t->d_binom); cudaFree(t->d_stream); cudaFree(t->d_partial);
     for (int c = 0; c < 6; ++c) cudaFree(t->d_stiles[c]);
     cudaFree(t->d_ko_stream); cudaFree(t->d_ko_ht); cudaFree(t->d_flags); cudaFree(t->d_perm);
     if (t->h_flags) cudaFreeHost(t->h_flags);

@@ -45,15 +45,17 @@ def _serial_columns(t, keys, col_pos):
 
 
 def _group_scale(xy, c, keys, col_pos):
-    """sum |c_k| of the group that couples row i to column j: the magnitude the partial sums of H[i, j] can reach."""
+    """(sum |c_k|, number of terms) of the group that couples row i to column j: the magnitude the partial sums of H[i, j] can
+    reach and the number of additions behind it."""
     xy0 = xy.reshape(len(xy), -1)[:, 0].astype(np.uint64)
-    u, inv = np.unique(xy0, return_inverse=True)
+    u, inv, counts = np.unique(xy0, return_inverse=True, return_counts=True)
     tot = np.zeros(len(u))
     np.add.at(tot, inv, np.abs(c))
     flips = keys[:, None] ^ keys[np.asarray(col_pos)][None, :]
     idx = np.searchsorted(u, flips)
     idx[idx >= len(u)] = 0
-    return np.where(u[idx] == flips, tot[idx], 0.0)
+    hit = u[idx] == flips
+    return np.where(hit, tot[idx], 0.0), np.where(hit, counts[idx], 0)
 
 
 CASES = [("LiH", True, None, 225, "all", "dense", False),      # dense table, per-row walk
@@ -85,10 +87,16 @@ def test_fused_matrix_elements_zero_set_and_ulp_drift(mol, sector, _, m, ncol, k
     serial, stored = _serial_columns(t, keys, col_pos)
     # (1) the exact-zero set of the fused path IS the serial one (stored <=> H != 0.0 exactly, hamiltonian.py:363)
     assert np.array_equal(fused != 0.0, stored), f"zero sets differ at {int((( fused != 0.0) != stored).sum())} entries"
-    # (2) drift of the chunked sums, in units of the last place of the largest partial sum a group can reach (sum |c_k|)
-    scale = _group_scale(xy, c, keys, col_pos)
+    # (2) drift of the chunked sums.  Serial order: n additions, each rounded to <= 0.5 ulp of the running sum (<= sum |c_k|);
+    # chunked order: the same number of additions inside the chunks (done on the host, reference order) plus one per chunk.  Two
+    # correctly rounded evaluations of the same sum therefore differ by at most 0.5 * (2 n + ceil(n / 6)) ulp of sum |c_k|; what
+    # the molecules actually show is far below it (<= 10 ulp for the 100+-term diagonal groups), asserted as a regression bar.
+    scale, n_terms = _group_scale(xy, c, keys, col_pos)
     ulps = np.abs(fused - serial)[stored] / np.spacing(scale[stored])
-    assert ulps.max(initial=0.0) <= 4.0, f"max drift {ulps.max():.2f} ulp of sum|c_k|"
+    n_st = n_terms[stored]
+    assert np.all(ulps <= 0.5 * (2 * n_st + np.ceil(n_st / 6.0))), "drift beyond the rounding-error bound of the two summation orders"
+    assert ulps.max(initial=0.0) <= 16.0, f"max drift {ulps.max():.2f} ulp of sum|c_k|"
+    assert np.all(ulps[n_st <= 30] <= 4.0)   # short groups: at most five chunk additions
     # groups of <= 6 terms come from LUT entries produced by the reference's own serial additions: bit-identical
     xy0 = xy.reshape(len(xy), -1)[:, 0].astype(np.uint64)
     u, counts = np.unique(xy0, return_counts=True)

@@ -210,6 +210,30 @@ def test_rows_and_hij_vs_oracle_bit_exact(mol, m, sector):
     assert np.array_equal(uniq, np.unique(c2[:, 0]))
 
 
+def test_rows_are_independent_of_the_table_chunking():
+    """The stored-row kernels cut the term table into 16 / 8 / 4 / 2 / 1 chunks on group boundaries depending on the batch size
+    (rows.cu rows_chunks_for): the CSR rows, dense H_ij and restricted column indices of the same states must not depend on it,
+    and equal the oracle's serial sums."""
+    nb200, c_oracle, eo = _mods()
+    t, ct, (N, na, nb) = make_tables("N2", sector=False)
+    rng = np.random.default_rng(77)
+    head = random_keys(N, 4000, seed=78)
+    i2, c2, v2 = ct.rows(head)
+    for m in (4000, 30000, 60000, 120000, 250000, 320000):   # 16, 16, 8, 4, 2, 1 chunks on a 148-SM device
+        st = np.concatenate([head, rng.integers(0, 2 ** N, size=m - len(head), dtype=np.int64).astype(np.uint64)])
+        indptr, cols, ridx, vals = t.rows(st)
+        n_head = int(indptr[len(head)].item())
+        assert np.array_equal(indptr[: len(head) + 1].cpu().numpy(), i2), m
+        assert np.array_equal(cols[:n_head].cpu().numpy().view(np.uint64), c2), m
+        assert np.array_equal(vals[:n_head].cpu().numpy(), v2), m
+        assert np.array_equal(ridx[:n_head].cpu().numpy(), ct.restricted_index(c2)), m
+        del indptr, cols, ridx, vals
+    ts, cts, (N, na, nb) = make_tables("N2", sector=True)
+    sec = random_sector_states(N, na, nb, 2500, seed=79)
+    a = ts.hij_dense(sec).cpu().numpy()
+    assert np.array_equal(a.reshape(-1), cts.hij_dense(sec))
+
+
 @pytest.mark.parametrize("N,K,M", [(40, 1500, 3000), (63, 4000, 2000), (64, 2000, 1500), (100, 3000, 2500), (127, 1000, 1000), (20, 30000, 500)])
 def test_wide_and_large_synthetic_tables(N, K, M):
     """64-/128-bit masks and tables larger than one shared-memory tile."""
