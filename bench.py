@@ -499,6 +499,12 @@ def main():
 
     wl = make_workload(args.workload, 0 if args.strong else rank, m_override=args.states, synth=tuple(args.synthetic))
     if args.strong and world > 1:  # every rank generated the same batch; keep this rank's contiguous block of rows
+        if wl["N"] <= 26:
+            # direct-address key spaces: KEY-RANGE shards (the batch in ascending key order, equal row counts per rank) — the
+            # key-order walk skips every 32-key task without a row of this rank, so its work shrinks with the shard
+            order = np.argsort(np.asarray(wl["states"]).reshape(-1), kind="stable")
+            wl["states"], wl["psi"] = np.asarray(wl["states"])[order], wl["psi"][order]
+            wl["desc"] += " — rows in ascending key order (key-range shards)"
         lo, hi = naqs_b200.distributed.shard_bounds(len(wl["states"]), world, rank)
         if (hi - lo) * world != len(wl["states"]):
             raise SystemExit("--strong needs a batch size divisible by the number of ranks")

@@ -203,7 +203,11 @@ int naqs_eloc_host_end(naqs_table_t* t);
  * Two passes: count -> (caller or naqs_exclusive_scan) -> fill.  A stored entry is a coupled state
  * that passes the sector filter with H != 0.0.  Columns of a row come in ascending unique-XY order.
  * d_col_ridx (optional, may be NULL) receives the restricted index of each column
- * (src/utils/hilbert.py:607-640 full2restricted_idx; = low key word without a sector). */
+ * (src/utils/hilbert.py:607-640 full2restricted_idx; = low key word without a sector).
+ * Small batches are walked with the term table cut into up to 16 chunks on XY-group boundaries (grid.y), so that a VMC
+ * sector of 10^4 states fills the GPU; every group is still summed by one thread in reference term order (bit-exact H).
+ * d_indptr of naqs_rows_fill must be the exclusive scan of naqs_rows_count's output for the SAME d_states contents; a fill
+ * that directly follows that count on this table (same d_states, n_states, stream) reuses its per-chunk counts. */
 int naqs_rows_count(naqs_table_t* t, const uint64_t* d_states, int64_t n_states, int64_t* d_counts, void* stream);
 int naqs_exclusive_scan(naqs_table_t* t, const int64_t* d_counts, int64_t n, int64_t* d_indptr /* n+1 */, void* stream);
 int naqs_rows_fill(naqs_table_t* t, const uint64_t* d_states, int64_t n_states, const int64_t* d_indptr,

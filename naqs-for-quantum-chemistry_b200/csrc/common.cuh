@@ -241,11 +241,22 @@ struct naqs_table {
     naqs::Tile* d_tiles = nullptr;
     int n_tiles = 0, tile_cap = 0;
     long long* d_binom = nullptr;  // C(n, k) table for the restricted-index ranker (lazy)
+    int32_t* d_rank_tab = nullptr; // per-spin rank tables (<= 32 qubits with a sector): [2^n_even | 2^n_odd] int32, built with d_binom
+    long long rank_n_b = 0;        // C(n_odd, n_beta)
     // stored-row kernels: the same terms cut into kMaxChunks chunks on group boundaries (grid.y of rows_kernel), so that a small
     // batch (a VMC sector: 10^4 rows) still fills the machine; row_chunk_lo[c] = first tile of base chunk c
     naqs::Tile* d_row_tiles = nullptr;
     int row_chunk_lo[naqs::kMaxChunks + 1] = {0};
     int n_row_chunks = 0, row_tile_cap = 0;
+    // per-(chunk, row) counts of the last chunked naqs_rows_count: a naqs_rows_fill for the same (d_states, M, stream) that follows
+    // it reuses them once instead of recounting (its indptr must stem from those counts anyway)
+    int32_t* d_row_cc = nullptr;
+    size_t row_cc_bytes = 0;
+    const void* row_cc_states = nullptr;
+    int64_t row_cc_M = 0;
+    int row_cc_chunks = 0;
+    cudaStream_t row_cc_stream = nullptr;
+    bool row_cc_valid = false;
     // sliced (v2) formulation: byte stream + tile lists for the 1024/512/256-thread launch shapes
     int algo = 0;                  // 0 = sliced (default), 1 = direct
     int f32 = 0;                   // naqs_table_set_precision(32): float32 accumulation of H_ij (direct formulation only)
@@ -290,8 +301,26 @@ struct naqs_table {
     size_t ws_bytes = 0;
     void* d_stage = nullptr;  // device staging for naqs_eloc_host
     size_t stage_bytes = 0;
-    void* h_pinned = nullptr;
+    void* h_pinned = nullptr;   // page-locked staging of the small-batch (CUDA graph) form of naqs_eloc_host
     size_t pinned_bytes = 0;
+    // small batches through naqs_eloc_host are launch-bound (ten stream operations for a 224-state LiH batch): the whole sequence —
+    // uploads from the page-locked staging, lookup build, fused kernel, download — is captured once per call signature into a
+    // CUDA graph and replayed.  An entry is valid only while every buffer it baked in is still the current one.
+    struct HostGraph {
+        int64_t sig[10] = {0};       // M, T, key_itemsize, psi_dtype, eloc_dtype, lookup_kind (with flags), own_table, algo, f32, 0
+        const void* ptrs[12] = {nullptr};
+        cudaGraphExec_t exec = nullptr;
+        bool failed = false;         // capture did not work for this signature: use the plain path
+        int64_t n_launches = 0;      // kernels in the graph (naqs_launch_count stays meaningful)
+        int64_t lookup_state[9] = {0};
+        unsigned long long last_use = 0;
+    };
+    std::vector<HostGraph> host_graphs;
+    unsigned long long host_graph_clock = 0;
+    bool env_no_graph = false;
+    const void* pending_out_src = nullptr;  // staged E_loc of a begun small-batch call -> copied to pending_out_dst in _end
+    void* pending_out_dst = nullptr;
+    size_t pending_out_bytes = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t last_stream = nullptr;  // stream of the last call that touched the per-table buffers (stream_handover)
     bool last_stream_valid = false;

@@ -289,17 +289,38 @@ __device__ __forceinline__ long long lex_rank(const uint32_t (&j)[NW], int start
     return r;
 }
 
+// Ranker inputs: the binomial table, and — for keys of <= 32 qubits — the rank of every alpha / beta occupation pattern
+// (tab_a[pattern of the even qubits], tab_b[pattern of the odd qubits], 2^ceil(N/2) / 2^floor(N/2) int32 entries): the analogue
+// of the reference's 2^N lookup table (hilbert.py:607-640) factorised per spin, two loads instead of a loop over the qubits.
+struct RankView {
+    const long long* binom;
+    const int32_t* tab_a;
+    const int32_t* tab_b;
+    long long n_b;  // C(n_odd, n_beta)
+};
+
+__device__ __forceinline__ uint32_t compress_even_bits(uint32_t x) {  // bits 0, 2, 4, ... -> bits 0, 1, 2, ...
+    x &= 0x55555555u;
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+    x = (x | (x >> 4)) & 0x00FF00FFu;
+    x = (x | (x >> 8)) & 0x0000FFFFu;
+    return x;
+}
+
 template <int NW>
-__device__ __forceinline__ long long restricted_index(const uint32_t (&j)[NW], const Sector& sec, const long long* __restrict__ binom) {
+__device__ __forceinline__ long long restricted_index(const uint32_t (&j)[NW], const Sector& sec, const RankView& rv) {
     if (!sec.enabled) {
         unsigned long long k0, k1;
         key_words64<NW>(j, k0, k1);
         return (long long)k0;
     }
     if (!in_sector<NW>(j, sec)) return -1;
+    if (NW == 1 && rv.tab_a)
+        return (long long)rv.tab_a[compress_even_bits(j[0])] * rv.n_b + (long long)rv.tab_b[compress_even_bits(j[0] >> 1)];
     const int n_even = (sec.n_qubits + 1) / 2, n_odd = sec.n_qubits / 2;
-    return lex_rank<NW>(j, 0, n_even, sec.n_alpha, binom) * binom[n_odd * 66 + sec.n_beta] +
-           lex_rank<NW>(j, 1, n_odd, sec.n_beta, binom);
+    return lex_rank<NW>(j, 0, n_even, sec.n_alpha, rv.binom) * rv.binom[n_odd * 66 + sec.n_beta] +
+           lex_rank<NW>(j, 1, n_odd, sec.n_beta, rv.binom);
 }
 
 // grid = (row blocks, table chunks).  A chunk is a contiguous range of tiles that starts and ends on a group boundary
@@ -309,7 +330,7 @@ __device__ __forceinline__ long long restricted_index(const uint32_t (&j)[NW], c
 template <int NW, int MODE, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 rows_kernel(TableView tv, const Tile* __restrict__ tiles, const __grid_constant__ ChunkBounds chunks, int n_chunks, int tile_cap, Sector sec,
-            const uint64_t* __restrict__ states, int64_t M, int words, const long long* __restrict__ binom,
+            const uint64_t* __restrict__ states, int64_t M, int words, RankView rank,
             int64_t* __restrict__ counts, int32_t* __restrict__ chunk_counts, const int64_t* __restrict__ indptr,
             uint64_t* __restrict__ col_keys, int64_t* __restrict__ col_ridx, double* __restrict__ vals) {
     uint32_t s[1][NW];
@@ -342,7 +363,7 @@ rows_kernel(TableView tv, const Tile* __restrict__ tiles, const __grid_constant_
             key_words64<NW>(j, k0, k1);
             col_keys[e * words] = k0;
             if (words > 1) col_keys[e * words + 1] = k1;
-            if (col_ridx) col_ridx[e] = restricted_index<NW>(j, sec, binom);
+            if (col_ridx) col_ridx[e] = restricted_index<NW>(j, sec, rank);
             vals[e] = h[0];
             ++e;
         }

@@ -37,7 +37,36 @@ int ensure_binom(naqs_table* t) {
         }
     NAQS_CUDA(cudaMalloc((void**)&t->d_binom, b.size() * sizeof(long long)));
     NAQS_CUDA(cudaMemcpy(t->d_binom, b.data(), b.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    // per-spin rank tables: rank of an occupation pattern among the C(n, k) combinations in itertools order (hilbert.py:446-469)
+    if (t->sector.enabled && t->nw32 == 1) {
+        const int n_even = (t->n_qubits + 1) / 2, n_odd = t->n_qubits / 2;
+        std::vector<int32_t> tab(((size_t)1 << n_even) + ((size_t)1 << n_odd), -1);
+        auto fill = [&](int32_t* dst, int n, int k) {
+            for (uint32_t v = 0; v < (1u << n); ++v) {
+                if (__builtin_popcount(v) != k) continue;
+                long long r = 0;
+                int seen = 0;
+                for (int p = 0; p < n && seen < k; ++p) {
+                    if ((v >> p) & 1u) ++seen;
+                    else r += b[(size_t)(n - 1 - p) * 66 + (size_t)(k - 1 - seen)];
+                }
+                dst[v] = (int32_t)r;
+            }
+        };
+        if (t->n_alpha <= n_even && t->n_beta <= n_odd && b[(size_t)n_even * 66 + t->n_alpha] < (1ll << 31) && b[(size_t)n_odd * 66 + t->n_beta] < (1ll << 31)) {
+            fill(tab.data(), n_even, t->n_alpha);
+            fill(tab.data() + ((size_t)1 << n_even), n_odd, t->n_beta);
+            NAQS_CUDA(cudaMalloc((void**)&t->d_rank_tab, tab.size() * sizeof(int32_t)));
+            NAQS_CUDA(cudaMemcpy(t->d_rank_tab, tab.data(), tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            t->rank_n_b = b[(size_t)n_odd * 66 + t->n_beta];
+        }
+    }
     return NAQS_OK;
+}
+
+RankView rank_view(const naqs_table* t) {
+    const int n_even = (t->n_qubits + 1) / 2;
+    return RankView{t->d_binom, t->d_rank_tab, t->d_rank_tab ? t->d_rank_tab + ((size_t)1 << n_even) : nullptr, t->rank_n_b};
 }
 
 // Number of table chunks (grid.y) for a batch of M rows: enough threads for about one full wave of resident threads, a power of
@@ -72,7 +101,7 @@ int launch_rows(naqs_table* t, const uint64_t* d_states, int64_t M, int n_chunks
     NAQS_SMEM_ATTR(kern, smem, t->device);
     const int64_t blocks = (M + kRowThreads - 1) / kRowThreads;
     kern<<<dim3((unsigned)blocks, (unsigned)n_chunks), kRowThreads, smem, stream>>>(t->view(), tiles, cb, n_chunks, cap, t->sector, d_states,
-                                                                                  M, t->words, t->d_binom, d_counts, d_chunk_counts, d_indptr,
+                                                                                  M, t->words, rank_view(t), d_counts, d_chunk_counts, d_indptr,
                                                                                   d_col_keys, d_col_ridx, d_vals);
     NAQS_LAUNCHED();
     return NAQS_OK;
@@ -88,24 +117,29 @@ int dispatch_rows(naqs_table* t, const uint64_t* d_states, int64_t M, int n_chun
     }
 }
 
-// per-(chunk, row) counts of a chunked launch live in the table's workspace: [n_chunks][M] int32
-int chunk_counts_ws(naqs_table* t, int n_chunks, int64_t M, int32_t** out) {
+// per-(chunk, row) counts of a chunked launch: [n_chunks][M] int32 in a buffer of their own (the caller's scan between
+// naqs_rows_count and naqs_rows_fill uses the generic workspace)
+int chunk_counts_buffer(naqs_table* t, int n_chunks, int64_t M, int32_t** out) {
     *out = nullptr;
     if (n_chunks <= 1) return NAQS_OK;
-    int rc = ensure_ws(t, (size_t)n_chunks * (size_t)M * sizeof(int32_t));
-    if (rc) return rc;
-    *out = reinterpret_cast<int32_t*>(t->d_ws);
+    const size_t bytes = (size_t)n_chunks * (size_t)M * sizeof(int32_t);
+    if (t->row_cc_bytes < bytes) {
+        cudaFree(t->d_row_cc); t->d_row_cc = nullptr; t->row_cc_bytes = 0;
+        NAQS_CUDA(cudaMalloc((void**)&t->d_row_cc, bytes));
+        t->row_cc_bytes = bytes;
+    }
+    *out = t->d_row_cc;
     return NAQS_OK;
 }
 
 template <int NW>
 __global__ void restricted_index_kernel(Sector sec, const uint64_t* __restrict__ keys, int64_t n,
-                                        const long long* __restrict__ binom, int64_t* __restrict__ out) {
+                                        RankView rank, int64_t* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t j[NW];
     load_key<NW>(keys, i, j);
-    out[i] = restricted_index<NW>(j, sec, binom);
+    out[i] = restricted_index<NW>(j, sec, rank);
 }
 
 }  // namespace
@@ -119,11 +153,14 @@ int naqs_rows_count(naqs_table_t* t, const uint64_t* d_states, int64_t M, int64_
     DeviceGuard guard(t->device);
     const int n_chunks = rows_chunks_for(t, M);
     int32_t* cc = nullptr;
-    if (int rc = chunk_counts_ws(t, n_chunks, M, &cc)) return rc;
+    t->row_cc_valid = false;
+    if (int rc = chunk_counts_buffer(t, n_chunks, M, &cc)) return rc;
     if (int rc = dispatch_rows<kRowsCount>(t, d_states, M, n_chunks, d_counts, cc, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream)) return rc;
     if (n_chunks > 1) {
         rows_sum_chunk_counts_kernel<<<(unsigned)((M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(cc, n_chunks, M, d_counts);
         NAQS_LAUNCHED();
+        t->row_cc_states = d_states; t->row_cc_M = M; t->row_cc_chunks = n_chunks; t->row_cc_stream = (cudaStream_t)stream;
+        t->row_cc_valid = true;
     }
     return NAQS_OK;
 }
@@ -135,12 +172,15 @@ int naqs_rows_fill(naqs_table_t* t, const uint64_t* d_states, int64_t M, const i
     if (M == 0) return NAQS_OK;
     DeviceGuard guard(t->device);
     if (d_col_ridx) { int rc = ensure_binom(t); if (rc) return rc; }
-    // a chunked fill needs the per-(chunk, row) counts: they are recomputed here (no state is carried over from naqs_rows_count,
-    // the caller's scan in between reuses the workspace)
+    // a chunked fill needs the per-(chunk, row) counts: those of the naqs_rows_count that produced this indptr when it was the last
+    // rows call on this table for the same (d_states, M, stream) — used once — otherwise they are recomputed here
     const int n_chunks = rows_chunks_for(t, M);
     int32_t* cc = nullptr;
-    if (int rc = chunk_counts_ws(t, n_chunks, M, &cc)) return rc;
-    if (n_chunks > 1)
+    const bool reuse = t->row_cc_valid && t->row_cc_states == d_states && t->row_cc_M == M && t->row_cc_chunks == n_chunks &&
+                       t->row_cc_stream == (cudaStream_t)stream;
+    t->row_cc_valid = false;
+    if (int rc = chunk_counts_buffer(t, n_chunks, M, &cc)) return rc;
+    if (n_chunks > 1 && !reuse)
         if (int rc = dispatch_rows<kRowsCount>(t, d_states, M, n_chunks, nullptr, cc, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream)) return rc;
     return dispatch_rows<kRowsFill>(t, d_states, M, n_chunks, nullptr, cc, d_indptr, d_col_keys, d_col_ridx, d_vals, (cudaStream_t)stream);
 }
@@ -163,9 +203,9 @@ int naqs_restricted_index(naqs_table_t* t, const uint64_t* d_keys, int64_t n, in
     const unsigned blocks = (unsigned)((n + 255) / 256);
     cudaStream_t st = (cudaStream_t)stream;
     switch (t->nw32) {
-        case 1: restricted_index_kernel<1><<<blocks, 256, 0, st>>>(t->sector, d_keys, n, t->d_binom, d_out); break;
-        case 2: restricted_index_kernel<2><<<blocks, 256, 0, st>>>(t->sector, d_keys, n, t->d_binom, d_out); break;
-        default: restricted_index_kernel<4><<<blocks, 256, 0, st>>>(t->sector, d_keys, n, t->d_binom, d_out); break;
+        case 1: restricted_index_kernel<1><<<blocks, 256, 0, st>>>(t->sector, d_keys, n, rank_view(t), d_out); break;
+        case 2: restricted_index_kernel<2><<<blocks, 256, 0, st>>>(t->sector, d_keys, n, rank_view(t), d_out); break;
+        default: restricted_index_kernel<4><<<blocks, 256, 0, st>>>(t->sector, d_keys, n, rank_view(t), d_out); break;
     }
     NAQS_LAUNCHED();
     return NAQS_OK;

@@ -398,6 +398,7 @@ int naqs_table_create(naqs_table_t** out, const uint64_t* h_xy, const uint64_t* 
     t->env_no_bin = getenv("NAQS_ELOC_NO_BIN") != nullptr;
     t->env_static_tasks = getenv("NAQS_ELOC_STATIC_TASKS") != nullptr;
     if (const char* e = getenv("NAQS_ELOC_CHUNKS")) t->env_chunks = atoi(e);
+    t->env_no_graph = getenv("NAQS_ELOC_NO_GRAPH") != nullptr;
 
     int rc = NAQS_OK;
     auto upload = [&](void** dptr, const void* src, size_t bytes) -> int {
@@ -452,8 +453,9 @@ int naqs_table_destroy(naqs_table_t* t) {
     cudaFree(t->d_yz); cudaFree(t->d_coeff); cudaFree(t->d_gxy); cudaFree(t->d_gstart);
     cudaFree(t->d_dense); cudaFree(t->d_dense32_raw); cudaFree(t->d_slots); cudaFree(t->d_buckets); cudaFree(t->d_filter); cudaFree(t->d_ws); cudaFree(t->d_stage);
     if (t->h_pinned) cudaFreeHost(t->h_pinned);
+    for (auto& g : t->host_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (t->own_stream) cudaStreamDestroy(t->own_stream);
-    cudaFree(t->d_tiles); cudaFree(t->d_row_tiles); cudaFree(t->d_binom); cudaFree(t->d_stream); cudaFree(t->d_partial);
+    cudaFree(t->d_tiles); cudaFree(t->d_row_tiles); cudaFree(t->d_binom); cudaFree(t->d_rank_tab); cudaFree(t->d_row_cc); cudaFree(t->d_stream); cudaFree(t->d_partial);
     for (int c = 0; c < 6; ++c) cudaFree(t->d_stiles[c]);
     cudaFree(t->d_ko_stream); cudaFree(t->d_ko_ht); cudaFree(t->d_flags); cudaFree(t->d_perm);
     if (t->h_flags) cudaFreeHost(t->h_flags);
@@ -1044,8 +1046,35 @@ int naqs_eloc_host_begin(naqs_table_t* t, const void* h_states, int key_itemsize
         NAQS_CUDA(cudaMalloc(&t->d_stage, total));
         t->stage_bytes = total;
     }
+    if (!t->h_flags) NAQS_CUDA(cudaHostAlloc((void**)&t->h_flags, sizeof(int), cudaHostAllocDefault));
     char* d = (char*)t->d_stage;
     cudaStream_t st = t->own_stream;
+    const size_t out_bytes = (size_t)M * (eloc_dtype == NAQS_C64 ? 8 : 16);
+    // small batch: stage through page-locked memory so that the stream sequence has fixed addresses and can be replayed as a graph
+    const size_t in_bytes = M * (kb_in + psz) + (own_table ? T * (kb_in + psz) : 0);
+    const bool small = !t->env_no_graph && st != nullptr && in_bytes + out_bytes <= ((size_t)1 << 19);
+    t->pending_out_dst = nullptr;
+    if (small) {
+        const size_t p_k = 0, p_p = al(M * kb_in), p_tk = p_p + al(M * psz), p_tp = p_tk + (own_table ? al(T * kb_in) : 0),
+                     p_out = p_tp + (own_table ? al(T * psz) : 0), p_total = p_out + al(out_bytes);
+        if (t->pinned_bytes < p_total) {
+            if (t->h_pinned) { NAQS_CUDA(cudaStreamSynchronize(st)); cudaFreeHost(t->h_pinned); }
+            t->h_pinned = nullptr; t->pinned_bytes = 0;
+            NAQS_CUDA(cudaHostAlloc(&t->h_pinned, std::max<size_t>(p_total, (size_t)1 << 16), cudaHostAllocDefault));
+            t->pinned_bytes = std::max<size_t>(p_total, (size_t)1 << 16);
+        }
+        char* hp = (char*)t->h_pinned;
+        std::memcpy(hp + p_k, h_states, M * kb_in);
+        std::memcpy(hp + p_p, h_psi, M * psz);
+        h_states = hp + p_k; h_psi = hp + p_p;
+        if (own_table) {
+            std::memcpy(hp + p_tk, h_tkeys, T * kb_in);
+            std::memcpy(hp + p_tp, h_tpsi, T * psz);
+            h_tkeys = hp + p_tk; h_tpsi = hp + p_tp;
+        }
+        t->pending_out_src = hp + p_out; t->pending_out_dst = h_eloc; t->pending_out_bytes = out_bytes;
+        h_eloc = hp + p_out;
+    }
     auto upload_keys = [&](const void* h, size_t o_raw, size_t o_64, int64_t n, const uint64_t** out) -> int {
         if (key_itemsize == 8) {
             NAQS_CUDA(cudaMemcpyAsync(d + o_64, h, n * kb, cudaMemcpyHostToDevice, st));
@@ -1057,31 +1086,102 @@ int naqs_eloc_host_begin(naqs_table_t* t, const void* h_states, int key_itemsize
         *out = (const uint64_t*)(d + o_64);
         return NAQS_OK;
     };
-    const uint64_t *d_keys = nullptr, *d_tk = nullptr;
-    int rc = upload_keys(h_states, o_kraw, o_k64, M, &d_keys);
-    if (rc) return rc;
-    NAQS_CUDA(cudaMemcpyAsync(d + o_psi, h_psi, M * psz, cudaMemcpyHostToDevice, st));
-    const void* d_tp = d + o_psi;
-    d_tk = d_keys;
-    if (own_table) {
-        rc = upload_keys(h_tkeys, o_tkraw, o_tk64, T, &d_tk);
+    auto enqueue = [&]() -> int {
+        const uint64_t *d_keys = nullptr, *d_tk = nullptr;
+        int rc = upload_keys(h_states, o_kraw, o_k64, M, &d_keys);
         if (rc) return rc;
-        NAQS_CUDA(cudaMemcpyAsync(d + o_tp, h_tpsi, T * psz, cudaMemcpyHostToDevice, st));
-        d_tp = d + o_tp;
+        NAQS_CUDA(cudaMemcpyAsync(d + o_psi, h_psi, M * psz, cudaMemcpyHostToDevice, st));
+        const void* d_tp = d + o_psi;
+        d_tk = d_keys;
+        if (own_table) {
+            rc = upload_keys(h_tkeys, o_tkraw, o_tk64, T, &d_tk);
+            if (rc) return rc;
+            NAQS_CUDA(cudaMemcpyAsync(d + o_tp, h_tpsi, T * psz, cudaMemcpyHostToDevice, st));
+            d_tp = d + o_tp;
+        }
+        rc = naqs_lookup_build(t, d_tk, d_tp, psi_dtype, T, lookup_kind, st);
+        if (rc) return rc;
+        rc = naqs_eloc(t, d_keys, d + o_psi, psi_dtype, M, (double*)(d + o_out), st);
+        if (rc) return rc;
+        if (eloc_dtype == NAQS_C64) {  // the reference hands E_loc to torch as float32 pairs (src/utils/complex.py:139-140)
+            narrow_eloc_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>((const double2*)(d + o_out), M, (float2*)(d + o_out32));
+            NAQS_LAUNCHED();
+            NAQS_CUDA(cudaMemcpyAsync(h_eloc, d + o_out32, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+        } else {
+            NAQS_CUDA(cudaMemcpyAsync(h_eloc, d + o_out, (size_t)M * 16, cudaMemcpyDeviceToHost, st));
+        }
+        NAQS_CUDA(cudaMemcpyAsync(t->h_flags, t->d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+        return NAQS_OK;
+    };
+    if (!small) return enqueue();
+
+    // ---- small batch: replay / capture the sequence as a CUDA graph -------------------------------------------------
+    using HostGraph = naqs_table::HostGraph;
+    auto lookup_state = [&](int64_t* s) {
+        s[0] = t->lookup_kind; s[1] = t->lookup_n; s[2] = t->dense32_valid; s[3] = (int64_t)(uintptr_t)t->d_dense32_ext; s[4] = t->filter_valid;
+        s[5] = t->filter_log2w; s[6] = t->filter_small_valid; s[7] = t->n_buckets; s[8] = t->hash_cap;
+    };
+    auto buffer_ptrs = [&](const void** q) {
+        q[0] = t->d_stage; q[1] = t->d_ws; q[2] = t->d_partial; q[3] = t->d_dense; q[4] = t->d_dense32; q[5] = t->d_buckets; q[6] = t->d_slots;
+        q[7] = t->d_filter; q[8] = t->d_perm; q[9] = t->h_pinned; q[10] = t->d_flags; q[11] = t->h_flags;
+    };
+    const int64_t sig[10] = {M, T, key_itemsize, psi_dtype, eloc_dtype, lookup_kind, own_table ? 1 : 0, t->algo, t->f32, 0};
+    HostGraph* g = nullptr;
+    for (auto& e : t->host_graphs)
+        if (std::memcmp(e.sig, sig, sizeof(sig)) == 0) { g = &e; break; }
+    const void* now[12];
+    buffer_ptrs(now);
+    if (g && g->exec && std::memcmp(g->ptrs, now, sizeof(now)) == 0) {
+        if (int rc_s = stream_handover(t, st)) return rc_s;
+        t->lookup_kind = (int)g->lookup_state[0]; t->lookup_n = g->lookup_state[1]; t->dense32_valid = g->lookup_state[2] != 0;
+        t->d_dense32_ext = reinterpret_cast<const float2*>((uintptr_t)g->lookup_state[3]); t->filter_valid = g->lookup_state[4] != 0;
+        t->filter_log2w = (int)g->lookup_state[5]; t->filter_small_valid = g->lookup_state[6] != 0; t->n_buckets = g->lookup_state[7]; t->hash_cap = g->lookup_state[8];
+        NAQS_CUDA(cudaGraphLaunch(g->exec, st));
+        g_launches.fetch_add(g->n_launches, std::memory_order_relaxed);
+        g->last_use = ++t->host_graph_clock;
+        return NAQS_OK;
     }
-    rc = naqs_lookup_build(t, d_tk, d_tp, psi_dtype, T, lookup_kind, st);
-    if (rc) return rc;
-    rc = naqs_eloc(t, d_keys, d + o_psi, psi_dtype, M, (double*)(d + o_out), st);
-    if (rc) return rc;
-    if (eloc_dtype == NAQS_C64) {  // the reference hands E_loc to torch as float32 pairs (src/utils/complex.py:139-140)
-        narrow_eloc_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>((const double2*)(d + o_out), M, (float2*)(d + o_out32));
-        NAQS_LAUNCHED();
-        NAQS_CUDA(cudaMemcpyAsync(h_eloc, d + o_out32, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
-    } else {
-        NAQS_CUDA(cudaMemcpyAsync(h_eloc, d + o_out, (size_t)M * 16, cudaMemcpyDeviceToHost, st));
+    if (!g) {  // first call with this signature: plain run (it allocates whatever the sequence needs), remember the signature
+        if (t->host_graphs.size() >= 8) {
+            size_t victim = 0;
+            for (size_t i = 1; i < t->host_graphs.size(); ++i) if (t->host_graphs[i].last_use < t->host_graphs[victim].last_use) victim = i;
+            if (t->host_graphs[victim].exec) { NAQS_CUDA(cudaStreamSynchronize(st)); cudaGraphExecDestroy(t->host_graphs[victim].exec); }
+            t->host_graphs.erase(t->host_graphs.begin() + (long)victim);
+        }
+        HostGraph e;
+        std::memcpy(e.sig, sig, sizeof(sig));
+        e.last_use = ++t->host_graph_clock;
+        t->host_graphs.push_back(e);
+        return enqueue();
     }
-    if (!t->h_flags) NAQS_CUDA(cudaHostAlloc((void**)&t->h_flags, sizeof(int), cudaHostAllocDefault));
-    NAQS_CUDA(cudaMemcpyAsync(t->h_flags, t->d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    g->last_use = ++t->host_graph_clock;
+    if (g->failed) return enqueue();
+    if (g->exec) { NAQS_CUDA(cudaStreamSynchronize(st)); cudaGraphExecDestroy(g->exec); g->exec = nullptr; }  // a buffer moved: capture again
+    // second call: capture.  Nothing allocates now (same sizes as the first call); should anything go wrong the plain path runs.
+    if (int rc_s = stream_handover(t, st)) return rc_s;
+    const int64_t launches_before = g_launches.load();
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+        const int rc = enqueue();
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        ok = rc == NAQS_OK && ce == cudaSuccess && graph != nullptr;
+    }
+    if (ok) ok = cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    const void* after[12];
+    buffer_ptrs(after);
+    if (ok && std::memcmp(after, now, sizeof(now)) != 0) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; ok = false; }
+    if (!ok) {
+        cudaGetLastError();
+        g->exec = nullptr; g->failed = true;
+        g_launches.store(launches_before);
+        return enqueue();
+    }
+    g->n_launches = g_launches.load() - launches_before;
+    std::memcpy(g->ptrs, now, sizeof(now));
+    lookup_state(g->lookup_state);
+    NAQS_CUDA(cudaGraphLaunch(g->exec, st));
     return NAQS_OK;
 }
 
@@ -1091,6 +1191,10 @@ int naqs_eloc_host_end(naqs_table_t* t) {
     DeviceGuard guard(t->device);
     cudaStream_t st = t->own_stream;
     NAQS_CUDA(cudaStreamSynchronize(st));
+    if (t->pending_out_dst) {
+        std::memcpy(t->pending_out_dst, t->pending_out_src, t->pending_out_bytes);
+        t->pending_out_dst = nullptr;
+    }
     if (*t->h_flags & 1) {
         *t->h_flags = 0;
         NAQS_CUDA(cudaMemsetAsync(t->d_flags, 0, sizeof(int), st));

@@ -97,3 +97,40 @@ def test_out_of_range_key_is_flagged_not_dereferenced():
     keep[3] = False
     ref = _lib.complex_from_pairs(t.local_energy(st[keep], psi[keep]))  # the bad key is simply absent from the table
     assert np.allclose(out[keep], ref, rtol=1e-13, atol=0) and np.all(np.isfinite(good))
+
+
+def test_small_host_batches_replay_a_cuda_graph():
+    """naqs_eloc_host with a small batch: first call plain, second call captured into a CUDA graph, later calls replay it
+    (table.cu).  Every call must see ITS inputs (staged through page-locked memory), whatever ran on the table in between."""
+    import naqs_b200
+    from oracle import c_oracle
+    from oracle import eloc_oracle as eo
+    xy, yz, c, N, na, nb = load_table("LiH")
+    t, ct = naqs_b200.DeviceTermTable(xy, yz, c, N, na, nb), c_oracle.COracleTable(xy, yz, c, N, na, nb)
+    sec = eo.sector_keys(N, na, nb)[:, 0].astype(np.uint64)
+    launches = []
+    for it in range(6):
+        st = np.random.default_rng(100 + it).permutation(sec)[:200 if it != 3 else 150]     # call 3 has another signature
+        psi = eo.synthetic_psi(len(st), seed=200 + it).astype(np.complex64)
+        before = naqs_b200.launch_count()
+        got = t.local_energy_host(st.astype(np.int16), psi, assume_unique=True, out_dtype=np.complex64)
+        launches.append(naqs_b200.launch_count() - before)
+        ref = ct.local_energy(st, psi.astype(np.complex128))
+        assert np.abs(got - ref.astype(np.complex64)).max() <= 2e-6 * np.abs(ref).max(), it
+        if it == 4:   # a device-API call with another batch rebuilds the lookup in between: the replay must not depend on it
+            other = sec[:77]
+            e = t.local_energy(other, eo.synthetic_psi(77, seed=1))
+            assert np.abs(naqs_b200._lib.complex_from_pairs(e) - ct.local_energy(other, eo.synthetic_psi(77, seed=1))).max() < 1e-10
+    assert launches[0] == launches[1] == launches[2] == launches[4] == launches[5] > 0   # replays are counted like plain runs
+    # complex128 in/out and an out-of-range key through the replayed graph
+    st = sec[:64].copy()
+    for it in range(4):
+        psi = eo.synthetic_psi(64, seed=300 + it)
+        got = t.local_energy_host(st, psi, assume_unique=True)
+        assert np.abs(got - ct.local_energy(st, psi)).max() <= 1e-12 * np.abs(got).max()
+    bad = st.copy()
+    bad[5] = np.uint64(1) << np.uint64(40)
+    with pytest.raises(IndexError):
+        t.local_energy_host(bad, eo.synthetic_psi(64, seed=9), assume_unique=True)
+    got = t.local_energy_host(st, eo.synthetic_psi(64, seed=303), assume_unique=True)   # and the table is usable afterwards
+    assert np.abs(got - ct.local_energy(st, eo.synthetic_psi(64, seed=303))).max() <= 1e-12 * np.abs(got).max()
