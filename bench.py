@@ -536,7 +536,7 @@ def main():
         """One pass of the hot path with device-resident inputs; returns the 5 statistics sums (device)."""
         if comm is not None:
             # (key, psi) of every rank -> lookup table of this rank, one collective entry (naqs_table_exchange)
-            comm.exchange(table, states, psi, flags=0x1000 if os.environ.get("NAQS_BENCH_ALLGATHER") else 0)
+            comm.exchange(table, states, psi, flags=0x1000 if os.environ.get("NAQS_BENCH_ALLGATHER") else int(os.environ.get("NAQS_BENCH_EXCHANGE_FLAGS", "0"), 0))
         elif world > 1 and allreduce_table:
             # small key space: the direct-address table itself is all-reduced (8 * 2^N bytes, independent of the rank count);
             # psi is a function of the state, so copies of a key on several ranks are identical
@@ -757,7 +757,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": wl["desc"], "states_per_gpu": M, "terms": K, "lookup_keys": T,
                        "parallelism": f"states sharded x{world}, Pauli table replicated" + (
-                           ((", naqs_table_exchange: (key, psi) pushed into every rank's 2^N-entry complex64 table over peer memory" if allreduce_table and not os.environ.get("NAQS_BENCH_ALLGATHER") else ", naqs_table_exchange: NCCL all-gather of (key, psi) + lookup build")
+                           ((", naqs_table_exchange: the ranks' 2^N-entry complex64 tables merged over peer memory (two-shot: P2P loads of one slice, P2P stores of the merged slice; push kernel for sparse shards)" if allreduce_table and not os.environ.get("NAQS_BENCH_ALLGATHER") else ", naqs_table_exchange: NCCL all-gather of (key, psi) + lookup build")
                             + " + naqs_stats_allreduce of 5 fp64 sums") if comm is not None else
                            ((", NCCL all-reduce (MAX) of the 2^N-entry complex64 amplitude table" if allreduce_table else ", NCCL all-gather of (key, psi)") + " + all-reduce of 5 fp64 sums" if world > 1 else "")),
                        "l2": "256 MB device memset between timed steps (L2 flush, untimed)", "timing": "CUDA events per step on the launching stream, max over ranks"},

@@ -115,7 +115,8 @@ typedef struct naqs_comm naqs_comm_t;
 #define NAQS_COMM_ID_BYTES 128
 #define NAQS_EXCHANGE_GATHER 0x1000 /* force the NCCL all-gather + lookup-build path */
 #define NAQS_EXCHANGE_PUSH 0x2000   /* direct-address table: force the push kernel */
-#define NAQS_EXCHANGE_REDUCE 0x4000 /* direct-address table: force the all-reduce (MAX) of the table */
+#define NAQS_EXCHANGE_REDUCE 0x4000 /* direct-address table: force the NCCL all-reduce (MAX) of the table */
+#define NAQS_EXCHANGE_MERGE 0x8000  /* direct-address table: force the two-shot merge over peer memory (the default for dense shards) */
 int naqs_comm_unique_id(void* id128);
 int naqs_comm_init(naqs_comm_t** out, const void* id128, int world_size, int rank, int device);
 int naqs_comm_from_nccl(naqs_comm_t** out, void* nccl_comm, int world_size, int rank, int device);
@@ -126,8 +127,11 @@ int naqs_comm_info(const naqs_comm_t* c, int* world_size, int* rank);
  *     rank (peer memory), raises a flag there and waits for its peers' flags — one kernel, no reduction (copies of a key on
  *     several ranks carry the same amplitude by contract), no host synchronisation; the table is then attached like
  *     naqs_lookup_attach_dense32.  The first call maps the peer regions (synchronous).  When the shards are DENSE
- *     (max_local * (world - 1) > 2^n_qubits / 2: a push would deliver more than the table holds) the table is all-reduced
- *     instead (fill with -0.0f, scatter, ncclAllReduce MAX on the int32 bit patterns): constant volume, reducible in the switch.
+ *     (max_local * (world - 1) > 2^n_qubits / 2: a push would deliver more than the table holds) the tables are MERGED
+ *     instead, as a two-shot all-reduce written over peer memory: every rank scatters its pairs into its own zeroed table,
+ *     rank r ORs slice r of every peer's table into its own (P2P loads) and stores the merged slice into every table (P2P
+ *     stores); two flag round trips, volume 2 (world - 1) / world tables per rank whatever the rank count.
+ *     NAQS_EXCHANGE_REDUCE selects round 1's form (fill with -0.0f, scatter, ncclAllReduce MAX on the int32 bit patterns).
  *   otherwise: NCCL all-gather of the shards padded to max_local (the largest shard, the same value on every rank), then one
  *     naqs_lookup_build with NAQS_LOOKUP_DUPLICATES_EQUAL; `flags` may carry NAQS_LOOKUP_DENSE / _HASH. */
 int naqs_table_exchange(naqs_table_t* t, naqs_comm_t* c, const uint64_t* d_keys, const void* d_psi, int psi_dtype, int64_t n_local,

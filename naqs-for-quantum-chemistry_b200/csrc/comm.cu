@@ -70,7 +70,8 @@ static NcclApi& nccl_api() {
 
 constexpr int kMaxRanks = 64;
 // Region layout (identical on every rank except for the table offsets, which each rank aligns in its own address space):
-//   [0, 1024)            flags: int32 [2 kinds][kMaxRanks] — kind 0 table exchange, kind 1 statistics; flag[k][r] = last epoch rank r completed
+//   [0, 1024)            flags: int32 [4 kinds][kMaxRanks] — kind 0 table push, kind 1 statistics, kind 2 "my pairs are in my table",
+//                        kind 3 "my slice of the merged table is in every table"; flag[k][r] = last epoch rank r completed
 //   [1024, 1024 + 8192)  statistics slots: double [2 parities][kMaxRanks][8]
 //   [16384, ...)         three direct-address complex64 tables (2^N entries each), each aligned to its size: two alternate
 //                        between the epochs of the push exchange, the third belongs to the all-reduce exchange
@@ -159,6 +160,106 @@ __global__ void push_stats_kernel(char* const* __restrict__ peer, int world, int
         double acc = 0.0;
         for (int r = 0; r < world; ++r) acc += slots[r * 8 + t];
         sums5[t] = acc;
+    }
+}
+
+// Dense shards (a rank's pairs alone fill a good part of the table): a push would deliver every pair to every peer (volume
+// ~ n_local * world); instead the tables are MERGED like a two-shot all-reduce written over peer memory.  Every rank scatters
+// its pairs into its OWN zeroed table and publishes flag kind 2 (scatter_signal_kernel).  Rank r then owns slice r of the key
+// space: it ORs slice r of every peer's table into its own (P2P vector loads over NVLink) and stores the merged slice back
+// into every peer's table (P2P stores), publishes flag kind 3 and waits for the kind-3 flags of its peers
+// (merge_table_kernel).  Bitwise OR is the exact merge: an absent entry is all-zero bits, and copies of a key on several
+// ranks carry the same amplitude by contract.  Volume per rank: 2 * (world - 1) / world tables whatever the rank count; two
+// flag round trips instead of a collective call.
+__global__ void scatter_signal_kernel(char* const* __restrict__ peer, const unsigned long long* __restrict__ table_off, int world, int rank, int parity,
+                                      const uint64_t* __restrict__ keys, const float2* __restrict__ psi, int64_t n, int64_t entries, int epoch,
+                                      int* __restrict__ done, int* __restrict__ err_flags) {
+    float2* own = reinterpret_cast<float2*>(peer[rank] + table_off[2 * rank + parity]);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long k = keys[i];
+        if (k >= (unsigned long long)entries) { if (err_flags) atomicOr(err_flags, 1); continue; }
+        own[k] = psi[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int last;
+    if (threadIdx.x == 0) last = atomicAdd(done, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x == 0) *done = 0;
+    __threadfence_system();
+    if ((int)threadIdx.x < world) st_flag(reinterpret_cast<int*>(peer[threadIdx.x] + kFlagsOff) + 2 * kMaxRanks + rank, epoch);
+}
+
+__device__ __forceinline__ uint4 ld_peer_v4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+template <int WORLD>  // 0: run-time rank count
+__global__ void __launch_bounds__(256) merge_table_kernel(char* const* __restrict__ peer, const unsigned long long* __restrict__ table_off, int world_rt, int rank,
+                                                          int parity, int64_t n_vec, int epoch, int* __restrict__ done) {
+    const int world = WORLD ? WORLD : world_rt;
+    __shared__ uint4* tab[kMaxRanks];
+    if ((int)threadIdx.x < world) {
+        tab[threadIdx.x] = reinterpret_cast<uint4*>(peer[threadIdx.x] + table_off[2 * threadIdx.x + parity]);
+        const int* mine = reinterpret_cast<const int*>(peer[rank] + kFlagsOff) + 2 * kMaxRanks + threadIdx.x;
+        while (ld_flag(mine) - epoch < 0) { }   // peer threadIdx.x has scattered its pairs of this epoch
+    }
+    __syncthreads();
+    const int64_t lo = n_vec * rank / world, hi = n_vec * (rank + 1) / world;
+    uint4* const own = tab[rank];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (WORLD) {
+        // BATCH vectors per thread and pass: every P2P load of the pass is in flight before the first one is consumed
+        constexpr int BATCH = WORLD <= 4 ? 4 : 2;
+        for (int64_t i0 = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += BATCH * stride) {
+            uint4 v[BATCH], in[BATCH][WORLD > 1 ? WORLD - 1 : 1];
+#pragma unroll
+            for (int b = 0; b < BATCH; ++b) {
+                const int64_t i = i0 + b * stride;
+                if (i < hi) {
+#pragma unroll
+                    for (int r = 1; r < WORLD; ++r) in[b][r - 1] = ld_peer_v4(tab[(rank + r) % WORLD] + i);
+                    v[b] = own[i];
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < BATCH; ++b) {
+                const int64_t i = i0 + b * stride;
+                if (i < hi) {
+#pragma unroll
+                    for (int r = 1; r < WORLD; ++r) { v[b].x |= in[b][r - 1].x; v[b].y |= in[b][r - 1].y; v[b].z |= in[b][r - 1].z; v[b].w |= in[b][r - 1].w; }
+                    own[i] = v[b];
+#pragma unroll
+                    for (int r = 1; r < WORLD; ++r) tab[(rank + r) % WORLD][i] = v[b];
+                }
+            }
+        }
+    } else {
+        for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
+            uint4 v = own[i];
+            for (int r = 1; r < world; ++r) {
+                const uint4 w = ld_peer_v4(tab[(rank + r) % world] + i);
+                v.x |= w.x; v.y |= w.y; v.z |= w.z; v.w |= w.w;
+            }
+            own[i] = v;
+            for (int r = 1; r < world; ++r) tab[(rank + r) % world][i] = v;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int last;
+    if (threadIdx.x == 0) last = atomicAdd(done, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x == 0) *done = 0;
+    __threadfence_system();
+    if ((int)threadIdx.x < world) {
+        st_flag(reinterpret_cast<int*>(peer[threadIdx.x] + kFlagsOff) + 3 * kMaxRanks + rank, epoch);
+        const int* mine = reinterpret_cast<const int*>(peer[rank] + kFlagsOff) + 3 * kMaxRanks + threadIdx.x;
+        while (ld_flag(mine) - epoch < 0) { }   // every slice of the merged table has landed here
     }
 }
 
@@ -314,9 +415,12 @@ int naqs_table_exchange(naqs_table_t* t, naqs_comm_t* c, const uint64_t* d_keys,
         const int64_t entries = 1ll << t->n_qubits;
         int rc = ensure_region(c, entries, st);
         if (rc) return rc;
-        // dense shards -> all-reduce of the table (see the header of this file); sparse shards -> push
-        const bool reduce = c->world > 1 && !(flags & NAQS_EXCHANGE_PUSH) &&
-                            ((flags & NAQS_EXCHANGE_REDUCE) || (double)max_local * (c->world - 1) > 0.5 * (double)entries);
+        // dense shards -> merge of the tables over peer memory (NAQS_EXCHANGE_REDUCE: the NCCL all-reduce (MAX) of round 1 instead);
+        // sparse shards -> push
+        const bool dense_shards = c->world > 1 && !(flags & NAQS_EXCHANGE_PUSH) &&
+                                  ((flags & (NAQS_EXCHANGE_REDUCE | NAQS_EXCHANGE_MERGE)) || (double)max_local * (c->world - 1) > 0.5 * (double)entries);
+        const bool reduce = dense_shards && (flags & NAQS_EXCHANGE_REDUCE) != 0;
+        const bool merge = dense_shards && !reduce && entries >= 2 * (int64_t)c->world;
         if (reduce) {
             float2* tbl = reinterpret_cast<float2*>(c->region + c->info[(size_t)c->rank].table_off[0] + 2 * (size_t)entries * sizeof(float2));
             fill_absent_kernel<<<4 * 148, 256, 0, st>>>(reinterpret_cast<int4*>(tbl), entries / 2);
@@ -330,14 +434,32 @@ int naqs_table_exchange(naqs_table_t* t, naqs_comm_t* c, const uint64_t* d_keys,
         }
         const unsigned e = ++c->epoch_table;
         const int cur = (int)(e & 1u), nxt = cur ^ 1;
-        // the table of the NEXT step is cleared now, before this rank signals epoch e: a peer only pushes step e + 1 after it has
-        // seen that signal (see the header of this file)
+        // the table of the NEXT step is cleared now, before this rank signals epoch e: a peer only writes into it in step e + 1,
+        // after it has seen that signal (see the header of this file)
         NAQS_CUDA(cudaMemsetAsync(c->region + c->info[(size_t)c->rank].table_off[nxt], 0, (size_t)entries * sizeof(float2), st));
         const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n_local + 255) / 256, 4 * 148));
+        const float* mine = reinterpret_cast<const float*>(c->region + c->info[(size_t)c->rank].table_off[cur]);
+        if (merge) {
+            scatter_signal_kernel<<<blocks, 256, 0, st>>>(c->d_peer, c->d_table_off, c->world, c->rank, cur, d_keys, reinterpret_cast<const float2*>(d_psi),
+                                                          n_local, entries, (int)e, c->d_done, t->d_flags);
+            NAQS_LAUNCHED();
+            const int64_t n_vec = entries / 2;
+            const unsigned mblocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n_vec / c->world + 255) / 256, 2 * 148));
+#define NAQS_MERGE(W) merge_table_kernel<W><<<mblocks, 256, 0, st>>>(c->d_peer, c->d_table_off, c->world, c->rank, cur, n_vec, (int)e, c->d_done)
+            switch (c->world) {
+                case 2: NAQS_MERGE(2); break;
+                case 4: NAQS_MERGE(4); break;
+                case 8: NAQS_MERGE(8); break;
+                default: NAQS_MERGE(0); break;
+            }
+#undef NAQS_MERGE
+            NAQS_LAUNCHED();
+            return naqs_lookup_attach_dense32(t, mine, entries);
+        }
         push_table_kernel<<<blocks, 256, 0, st>>>(c->d_peer, c->d_table_off, c->world, c->rank, cur, d_keys, reinterpret_cast<const float2*>(d_psi), n_local,
                                                   entries, (int)e, c->d_done, t->d_flags);
         NAQS_LAUNCHED();
-        return naqs_lookup_attach_dense32(t, reinterpret_cast<const float*>(c->region + c->info[(size_t)c->rank].table_off[cur]), entries);
+        return naqs_lookup_attach_dense32(t, mine, entries);
     }
     // large key spaces: NCCL all-gather of equally sized (padded) shards, then one lookup build over the valid pairs.
     // max_local = the largest shard (every rank passes the same value); a shorter shard is padded with an out-of-range key,

@@ -613,9 +613,10 @@ def _mgpu_worker(rank, world, port, q):
         t_push = naqs_b200.DeviceTermTable(xy, yz, c, N, na, nb, device=f"cuda:{rank}")
         sizes = [nd.shard_bounds(len(st), world, r) for r in range(world)]
         max_local = max(b - a for a, b in sizes)
-        for rep in range(3):  # several epochs: the two peer tables alternate and are cleared in between
+        modes = (0, 0x2000, 0x4000, 0x8000, 0x8000, 0x2000, 0x8000)  # auto, push, NCCL all-reduce, merge, merge, push, merge
+        for rep in range(len(modes)):  # several epochs: the two peer tables alternate and are cleared in between, whatever the mode
             ps = psi * np.complex64(2.0 ** rep)  # exact in float32: E_loc is scale invariant
-            e5, s5 = nd.sharded_local_energy_comm(t_push, comm, st[lo:hi], ps[lo:hi], flags=(0, 0x2000, 0x4000)[rep])  # auto, push, all-reduce
+            e5, s5 = nd.sharded_local_energy_comm(t_push, comm, st[lo:hi], ps[lo:hi], flags=modes[rep])
             diff = float((e5 - eloc).abs().max() / eloc.abs().max())
             assert diff < 1e-13, (rep, diff)
             st5 = nd.stats_from_sums(s5.cpu().numpy())
