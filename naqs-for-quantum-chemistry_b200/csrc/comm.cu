@@ -100,6 +100,15 @@ struct naqs_comm {
     // NCCL path (hash lookup): gather buffers
     void* d_gather = nullptr;
     size_t gather_bytes = 0;
+    // push-gather path (hash lookup, the default): a second peer-mapped region holding, per parity, the (key, psi) slots of all ranks
+    char* gregion = nullptr;
+    size_t gregion_bytes = 0;
+    int64_t g_cap = 0;              // entries per rank slot
+    size_t g_kb = 0, g_pb = 0;      // bytes per key / per amplitude the region was laid out for
+    std::vector<char*> gpeer;
+    char** d_gpeer = nullptr;
+    int* d_gdone = nullptr;
+    unsigned epoch_gather = 0;
 };
 
 namespace naqs {
@@ -337,6 +346,92 @@ static int ensure_region(naqs_comm* c, int64_t entries, cudaStream_t st) {
     return comm_sync_barrier(c, st);  // every region is zeroed and mapped before anyone pushes
 }
 
+// Large key spaces (hash lookup): every rank stores its (key, psi) pairs — padded to the slot capacity with all-ones keys, which
+// the lookup build skips — straight into its slot of EVERY rank's gather buffer, publishes flag kind 0 and waits for its peers:
+// the all-gather of the shards as one push kernel over peer memory (no NCCL call, no staging copies).
+// Layout per parity: keys [world][cap][kw] u64 | psi [world][cap][pw] u64.
+__global__ void push_pairs_kernel(char* const* __restrict__ peer, int world, int rank, unsigned long long keys_off, unsigned long long psi_off, int64_t cap,
+                                  int kw, int pw, const uint64_t* __restrict__ keys, const uint64_t* __restrict__ psi, int64_t n_local, int epoch,
+                                  int* __restrict__ done) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t k[2] = {~0ull, ~0ull}, v[2] = {0ull, 0ull};
+        if (i < n_local) {
+            for (int w = 0; w < kw; ++w) k[w] = keys[i * kw + w];
+            for (int w = 0; w < pw; ++w) v[w] = psi[i * pw + w];
+        }
+        for (int r = 0; r < world; ++r) {
+            const int rr = (rank + r) % world;
+            uint64_t* dk = reinterpret_cast<uint64_t*>(peer[rr] + keys_off) + ((int64_t)rank * cap + i) * kw;
+            uint64_t* dv = reinterpret_cast<uint64_t*>(peer[rr] + psi_off) + ((int64_t)rank * cap + i) * pw;
+            for (int w = 0; w < kw; ++w) dk[w] = k[w];
+            for (int w = 0; w < pw; ++w) dv[w] = v[w];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int last;
+    if (threadIdx.x == 0) last = atomicAdd(done, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x == 0) *done = 0;
+    __threadfence_system();
+    if ((int)threadIdx.x < world) {
+        st_flag(reinterpret_cast<int*>(peer[threadIdx.x] + kFlagsOff) + rank, epoch);
+        const int* mine = reinterpret_cast<const int*>(peer[rank] + kFlagsOff) + threadIdx.x;
+        while (ld_flag(mine) - epoch < 0) { }
+    }
+}
+
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// (Re)create the gather region for slots of `cap` entries.  Collective and synchronous (first exchange, or the batch outgrew it).
+static int ensure_gather_region(naqs_comm* c, int64_t max_local, size_t kb, size_t pb, cudaStream_t st) {
+    if (c->gregion && c->g_cap >= max_local && c->g_kb == kb && c->g_pb == pb) return NAQS_OK;
+    if (c->gregion) {  // every rank arrives here in the same call (max_local is the same everywhere): unmap, then free
+        NAQS_CUDA(cudaStreamSynchronize(st));
+        int rc = comm_sync_barrier(c, st);
+        if (rc) return rc;
+        for (int r = 0; r < (int)c->gpeer.size(); ++r)
+            if (r != c->rank && c->gpeer[(size_t)r]) cudaIpcCloseMemHandle(c->gpeer[(size_t)r]);
+        c->gpeer.clear();
+        rc = comm_sync_barrier(c, st);
+        if (rc) return rc;
+        cudaFree(c->gregion); c->gregion = nullptr;
+        cudaFree(c->d_gpeer); c->d_gpeer = nullptr;
+    }
+    const int64_t cap = std::max<int64_t>(1024, max_local + max_local / 4);
+    const size_t per_parity = al256((size_t)c->world * cap * kb) + al256((size_t)c->world * cap * pb);
+    const size_t bytes = kTablesOff + 2 * per_parity;
+    NAQS_CUDA(cudaMalloc((void**)&c->gregion, bytes));
+    NAQS_CUDA(cudaMemsetAsync(c->gregion, 0, kTablesOff, st));
+    c->gregion_bytes = bytes; c->g_cap = cap; c->g_kb = kb; c->g_pb = pb;
+    c->epoch_gather = 0;
+    cudaIpcMemHandle_t mine;
+    NAQS_CUDA(cudaIpcGetMemHandle(&mine, c->gregion));
+    cudaIpcMemHandle_t* d_h = nullptr;
+    NAQS_CUDA(cudaMalloc((void**)&d_h, sizeof(mine) * c->world));
+    NAQS_CUDA(cudaMemcpyAsync(d_h + c->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+    NAQS_NCCL(nccl_api().AllGather(d_h + c->rank, d_h, sizeof(mine), ncclUint8, c->nccl, st));
+    std::vector<cudaIpcMemHandle_t> all((size_t)c->world);
+    NAQS_CUDA(cudaMemcpyAsync(all.data(), d_h, sizeof(mine) * c->world, cudaMemcpyDeviceToHost, st));
+    NAQS_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_h);
+    c->gpeer.assign((size_t)c->world, nullptr);
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank) { c->gpeer[(size_t)r] = c->gregion; continue; }
+        void* p = nullptr;
+        NAQS_CUDA(cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess));
+        c->gpeer[(size_t)r] = static_cast<char*>(p);
+    }
+    NAQS_CUDA(cudaMalloc((void**)&c->d_gpeer, sizeof(char*) * c->world));
+    NAQS_CUDA(cudaMemcpyAsync(c->d_gpeer, c->gpeer.data(), sizeof(char*) * c->world, cudaMemcpyHostToDevice, st));
+    if (!c->d_gdone) {
+        NAQS_CUDA(cudaMalloc((void**)&c->d_gdone, sizeof(int)));
+        NAQS_CUDA(cudaMemsetAsync(c->d_gdone, 0, sizeof(int), st));
+    }
+    return comm_sync_barrier(c, st);  // every region is zeroed and mapped before anyone pushes
+}
+
 }  // namespace naqs
 
 using namespace naqs;
@@ -390,7 +485,10 @@ int naqs_comm_destroy(naqs_comm_t* c) {
     cudaDeviceSynchronize();
     for (int r = 0; r < (int)c->peer.size(); ++r)
         if (r != c->rank && c->peer[(size_t)r]) cudaIpcCloseMemHandle(c->peer[(size_t)r]);
+    for (int r = 0; r < (int)c->gpeer.size(); ++r)
+        if (r != c->rank && c->gpeer[(size_t)r]) cudaIpcCloseMemHandle(c->gpeer[(size_t)r]);
     cudaFree(c->region); cudaFree(c->d_peer); cudaFree(c->d_table_off); cudaFree(c->d_done); cudaFree(c->d_gather);
+    cudaFree(c->gregion); cudaFree(c->d_gpeer); cudaFree(c->d_gdone);
     if (c->own_nccl && c->nccl) nccl_api().CommDestroy(c->nccl);
     delete c;
     return NAQS_OK;
@@ -461,7 +559,29 @@ int naqs_table_exchange(naqs_table_t* t, naqs_comm_t* c, const uint64_t* d_keys,
         NAQS_LAUNCHED();
         return naqs_lookup_attach_dense32(t, mine, entries);
     }
-    // large key spaces: NCCL all-gather of equally sized (padded) shards, then one lookup build over the valid pairs.
+    // large key spaces: the shards are gathered by a push kernel over peer memory (push_pairs_kernel), then one lookup build over
+    // the valid pairs; NAQS_EXCHANGE_GATHER selects the NCCL all-gather of round 1 instead
+    NAQS_REQUIRE(max_local >= n_local, NAQS_ERR_ARG, "naqs_table_exchange: max_local must be the largest shard size of all ranks");
+    if (c->world == 1)
+        return naqs_lookup_build(t, d_keys, d_psi, psi_dtype, n_local, (flags & 0xff) | NAQS_LOOKUP_DUPLICATES_EQUAL, st);
+    if (!(flags & NAQS_EXCHANGE_GATHER)) {
+        const size_t kb = (size_t)8 * t->words, pb = psi_dtype == NAQS_C64 ? 8 : 16;
+        int rc = ensure_gather_region(c, max_local, kb, pb, st);
+        if (rc) return rc;
+        const unsigned e = ++c->epoch_gather;
+        const size_t per_parity = al256((size_t)c->world * c->g_cap * kb) + al256((size_t)c->world * c->g_cap * pb);
+        const size_t keys_off = kTablesOff + (size_t)(e & 1u) * per_parity, psi_off = keys_off + al256((size_t)c->world * c->g_cap * kb);
+        const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((c->g_cap + 255) / 256, 2 * 148));
+        push_pairs_kernel<<<blocks, 256, 0, st>>>(c->d_gpeer, c->world, c->rank, keys_off, psi_off, c->g_cap, (int)(kb / 8), (int)(pb / 8), d_keys,
+                                                  reinterpret_cast<const uint64_t*>(d_psi), n_local, (int)e, c->d_gdone);
+        NAQS_LAUNCHED();
+        t->quiet_range_flag = true;  // padding keys are out of range on purpose
+        rc = naqs_lookup_build(t, reinterpret_cast<const uint64_t*>(c->gregion + keys_off), c->gregion + psi_off, psi_dtype, (int64_t)c->world * c->g_cap,
+                               (flags & 0xff) | NAQS_LOOKUP_DUPLICATES_EQUAL, st);
+        t->quiet_range_flag = false;
+        return rc;
+    }
+    // NCCL all-gather of equally sized (padded) shards, then one lookup build over the valid pairs.
     // max_local = the largest shard (every rank passes the same value); a shorter shard is padded with an out-of-range key,
     // which the build kernels skip (NAQS_EXCHANGE_PADDED tells naqs_table_check not to report it).
     NAQS_REQUIRE(max_local >= n_local, NAQS_ERR_ARG, "naqs_table_exchange: max_local must be the largest shard size of all ranks");
@@ -500,9 +620,9 @@ int naqs_stats_allreduce(naqs_comm_t* c, double* d_sums5, void* stream_) {
     if (c->world == 1) return NAQS_OK;
     DeviceGuard guard(c->device);
     cudaStream_t st = (cudaStream_t)stream_;
-    if (c->region) {  // peer-mapped region available: one push kernel
+    if (c->region || c->gregion) {  // a peer-mapped region is available: one push kernel (flags / slots of that region)
         const unsigned e = ++c->epoch_stats;
-        push_stats_kernel<<<1, 64, 0, st>>>(c->d_peer, c->world, c->rank, (int)(e & 1u), d_sums5, (int)e);
+        push_stats_kernel<<<1, 64, 0, st>>>(c->region ? c->d_peer : c->d_gpeer, c->world, c->rank, (int)(e & 1u), d_sums5, (int)e);
         NAQS_LAUNCHED();
         return NAQS_OK;
     }

@@ -32,7 +32,9 @@ def load_terms_json(mol):
 
 
 CASE_TABLE = {"LiH_sector": "LiH", "LiH_small": "LiH", "H2O_sector": "H2O", "NH3_1000": "NH3", "N2_2000": "N2",
-              "N2_1.5_500": "N2_1.5", "N2_full_3000": "N2", "LiH_full_600": "LiH"}
+              "N2_1.5_500": "N2_1.5", "N2_full_3000": "N2", "LiH_full_600": "LiH",
+              # 30 qubits, the largest molecule of the paper: produced by the reference's own _HilbertRestricted (2^30-entry LUT, paid once)
+              "Li2O_500": "Li2O"}
 # the same seeded batches through PauliHamiltonian.get(dtype=np.float32), the reference constructor's default
 F32_CASE_TABLE = {"LiH_sector_f32": "LiH", "H2O_300_f32": "H2O", "N2_full_1000_f32": "N2"}
 
