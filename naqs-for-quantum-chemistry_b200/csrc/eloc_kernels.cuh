@@ -231,11 +231,15 @@ __device__ __forceinline__ void load_states(const uint64_t* __restrict__ states,
     }
 }
 
+// grid = (state blocks, table chunks): with more than one chunk (small batches: the chunk list of the stored-row kernels, cut on
+// group boundaries) the raw row sums of chunk c go to partial[c * M + m] and eloc_finalize_kernel adds them in chunk order.
 template <int NW, int R, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-eloc_direct_kernel(TableView tv, const Tile* __restrict__ tiles, int n_tiles, int tile_cap, Sector sec, LookupView lv,
-                   const uint64_t* __restrict__ states, const void* __restrict__ psi, int psi_dtype, int64_t M,
-                   double2* __restrict__ out) {
+eloc_direct_kernel(TableView tv, const Tile* __restrict__ tiles_all, const __grid_constant__ ChunkBounds chunks, int n_chunks, int tile_cap, Sector sec,
+                   LookupView lv, const uint64_t* __restrict__ states, const void* __restrict__ psi, int psi_dtype, int64_t M,
+                   double2* __restrict__ out, double2* __restrict__ partial) {
+    const Tile* tiles = tiles_all + chunks.lo[blockIdx.y];
+    const int n_tiles = chunks.lo[blockIdx.y + 1] - chunks.lo[blockIdx.y];
     uint32_t s[R][NW];
     bool valid[R];
     load_states<NW, R, THREADS>(states, M, s, valid);
@@ -265,7 +269,9 @@ eloc_direct_kernel(TableView tv, const Tile* __restrict__ tiles, int n_tiles, in
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int64_t m = base + (int64_t)r * THREADS;
-        if (valid[r]) out[m] = finalize_row(make_double2(e_re[r], e_im[r]), psi, psi_dtype, m);
+        if (!valid[r]) continue;
+        if (n_chunks > 1) partial[(int64_t)blockIdx.y * M + m] = make_double2(e_re[r], e_im[r]);
+        else out[m] = finalize_row(make_double2(e_re[r], e_im[r]), psi, psi_dtype, m);
     }
 }
 

@@ -599,15 +599,42 @@ template <int NW>
 static int launch_eloc(naqs_table_t* t, const uint64_t* d_states, const void* d_psi, int psi_dtype, int64_t M,
                        double* d_eloc, cudaStream_t stream) {
     constexpr int R = 4;
-    const size_t smem = tile_smem_bytes<NW>(t->tile_cap);
-    auto kern = eloc_direct_kernel<NW, R, kThreads>;
-    NAQS_SMEM_ATTR(kern, smem, t->device);
     const int64_t per_block = (int64_t)kThreads * R;
     const int64_t blocks = (M + per_block - 1) / per_block;
-    kern<<<(unsigned)blocks, kThreads, smem, stream>>>(t->view(), t->d_tiles, t->n_tiles, t->tile_cap,
-                                                      t->sector, t->lookup(), d_states, d_psi, psi_dtype, M,
-                                                      reinterpret_cast<double2*>(d_eloc));
+    // small batches: split the table into chunks on group boundaries (the list of the stored-row kernels) until about one
+    // wave of threads is resident; partial sums are added in chunk order (deterministic)
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, t->device);
+    int n_chunks = 1;
+    while (t->n_row_chunks > 0 && n_chunks < t->n_row_chunks && (int64_t)n_chunks * blocks * kThreads < (int64_t)sm_count * 2048) n_chunks *= 2;
+    ChunkBounds cb;
+    const Tile* tiles = t->d_tiles;
+    int cap = t->tile_cap;
+    if (n_chunks > 1) {
+        const int merge = t->n_row_chunks / n_chunks;
+        for (int c = 0; c <= kMaxChunks; ++c) cb.lo[c] = t->row_chunk_lo[std::min(c * merge, t->n_row_chunks)];
+        tiles = t->d_row_tiles;
+        cap = t->row_tile_cap;
+        const size_t need = (size_t)n_chunks * M * sizeof(double2);
+        if (t->partial_bytes < need) {
+            cudaFree(t->d_partial); t->d_partial = nullptr; t->partial_bytes = 0;
+            NAQS_CUDA(cudaMalloc((void**)&t->d_partial, need));
+            t->partial_bytes = need;
+        }
+    } else {
+        cb.lo[0] = 0;
+        for (int c = 1; c <= kMaxChunks; ++c) cb.lo[c] = t->n_tiles;
+    }
+    const size_t smem = tile_smem_bytes<NW>(cap);
+    auto kern = eloc_direct_kernel<NW, R, kThreads>;
+    NAQS_SMEM_ATTR(kern, smem, t->device);
+    kern<<<dim3((unsigned)blocks, (unsigned)n_chunks), kThreads, smem, stream>>>(t->view(), tiles, cb, n_chunks, cap, t->sector, t->lookup(), d_states,
+                                                                               d_psi, psi_dtype, M, reinterpret_cast<double2*>(d_eloc), t->d_partial);
     NAQS_LAUNCHED();
+    if (n_chunks > 1) {
+        eloc_finalize_kernel<<<(unsigned)((M + 255) / 256), 256, 0, stream>>>(t->d_partial, n_chunks, d_psi, psi_dtype, M, reinterpret_cast<double2*>(d_eloc));
+        NAQS_LAUNCHED();
+    }
     return NAQS_OK;
 }
 
