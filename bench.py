@@ -137,6 +137,22 @@ def make_workload(name, rank, m_override=None, synth=None):
     raise SystemExit(f"unknown workload {name}")
 
 
+def strong_shard(wl, world, rank, shard_bounds):
+    """--strong: ONE batch split over the ranks (in place).  Direct-address key spaces (N <= 26) get KEY-RANGE shards — the batch in
+    ascending key order, equal row counts per rank — so that the key-order walk skips every 32-key task without a row of this rank
+    and its work shrinks with the shard; hash-lookup batches keep contiguous blocks of the generated order."""
+    if wl["N"] <= 26:
+        order = np.argsort(np.asarray(wl["states"]).reshape(-1), kind="stable")
+        wl["states"], wl["psi"] = np.asarray(wl["states"])[order], wl["psi"][order]
+        wl["desc"] += " — rows in ascending key order (key-range shards)"
+    lo, hi = shard_bounds(len(wl["states"]), world, rank)
+    if (hi - lo) * world != len(wl["states"]):
+        raise SystemExit("--strong needs a batch size divisible by the number of ranks")
+    wl["states"], wl["psi"] = wl["states"][lo:hi], wl["psi"][lo:hi]
+    wl["desc"] += f" — STRONG scaling: the batch is split over {world} ranks"
+    return wl
+
+
 # ----------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     """Samples SM clock + throttle reasons of one GPU (NVML) while the timed region runs."""
@@ -498,18 +514,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     wl = make_workload(args.workload, 0 if args.strong else rank, m_override=args.states, synth=tuple(args.synthetic))
-    if args.strong and world > 1:  # every rank generated the same batch; keep this rank's contiguous block of rows
-        if wl["N"] <= 26:
-            # direct-address key spaces: KEY-RANGE shards (the batch in ascending key order, equal row counts per rank) — the
-            # key-order walk skips every 32-key task without a row of this rank, so its work shrinks with the shard
-            order = np.argsort(np.asarray(wl["states"]).reshape(-1), kind="stable")
-            wl["states"], wl["psi"] = np.asarray(wl["states"])[order], wl["psi"][order]
-            wl["desc"] += " — rows in ascending key order (key-range shards)"
-        lo, hi = naqs_b200.distributed.shard_bounds(len(wl["states"]), world, rank)
-        if (hi - lo) * world != len(wl["states"]):
-            raise SystemExit("--strong needs a batch size divisible by the number of ranks")
-        wl["states"], wl["psi"] = wl["states"][lo:hi], wl["psi"][lo:hi]
-        wl["desc"] += f" — STRONG scaling: the batch is split over {world} ranks"
+    if args.strong and world > 1:  # every rank generated the same batch; keep this rank's block of rows
+        strong_shard(wl, world, rank, naqs_b200.distributed.shard_bounds)
     table = naqs_b200.DeviceTermTable(wl["xy"], wl["yz"], wl["c"], wl["N"], wl["na"], wl["nb"], device=dev)
     M, K, W = len(wl["states"]), table.K, table.words
     h_states = torch.from_numpy(np.ascontiguousarray(wl["states"]).reshape(M, W).view(np.int64)).pin_memory()

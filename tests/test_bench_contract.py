@@ -60,3 +60,15 @@ def test_bench_helpers():
     assert all(bin(int(k) & ev30).count("1") == 7 and bin(int(k) & (ev30 << 1)).count("1") == 7 for k in st[:50])
     xy, yz, c = b.synthetic_table(70, 120)
     assert xy.shape == (120, 2) and yz.shape == (120, 2) and c.shape == (120,)
+    assert not (xy & yz).any()                          # a flipped qubit never carries a phase bit in the generator
+    # --strong: key-range shards for direct-address key spaces, contiguous blocks otherwise; the shards tile the batch
+    from naqs_b200.distributed import shard_bounds
+    full = b.make_workload("n2_1e6", 0, m_override=4000)
+    parts = [b.strong_shard(b.make_workload("n2_1e6", 0, m_override=4000), 4, r, shard_bounds) for r in range(4)]
+    keys = [np.asarray(p["states"]).reshape(-1) for p in parts]
+    assert all(len(k) == 1000 for k in keys) and all(keys[r].max() < keys[r + 1].min() for r in range(3))
+    assert np.array_equal(np.sort(np.concatenate(keys)), np.sort(np.asarray(full["states"]).reshape(-1)))
+    for p in parts:  # psi travels with its key
+        assert np.array_equal(p["psi"], b.psi_of_keys(p["states"], full["N"]))
+    li = [b.strong_shard(b.make_workload("li2o_1e5", 0, m_override=600), 2, r, shard_bounds) for r in range(2)]
+    assert np.array_equal(np.concatenate([np.asarray(p["states"]).reshape(-1) for p in li]), b.make_workload("li2o_1e5", 0, m_override=600)["states"].reshape(-1))
