@@ -87,7 +87,7 @@ for name in sorted(os.listdir(P)):
         d = last_json(name)
         chk = (d.get("check") or {}).get("multi_gpu_vs_single_rank") or {}
         wl = "Li2O 1e5" if "li2o" in name else "N2 1e6"
-        mode = ("strong" if d["scaling"] == "strong" else "weak") + (", NCCL all-reduce form" if "nccl" in name else "")
+        mode = ("strong" if d["scaling"] == "strong" else "weak") + (", round-1 NCCL form of the exchange" if "nccl" in name else "")
         w(f"| `{name}` | {wl}, {mode} | {d['n_gpus']} | {d['value']:.3e} | {d['ms_per_step']:.4f} | {d['roofline']['kernel_ms']:.4f} | {'ok' if chk.get('ok') else chk} |")
 if have(f"{R}_exchange_probe_g8.json"):
     pr = last_json(f"{R}_exchange_probe_g8.json")
