@@ -542,7 +542,7 @@ def main():
         """One pass of the hot path with device-resident inputs; returns the 5 statistics sums (device)."""
         if comm is not None:
             # (key, psi) of every rank -> lookup table of this rank, one collective entry (naqs_table_exchange)
-            comm.exchange(table, states, psi, flags=0x1000 if os.environ.get("NAQS_BENCH_ALLGATHER") else int(os.environ.get("NAQS_BENCH_EXCHANGE_FLAGS", "0"), 0))
+            comm.exchange(table, states, psi, max_local=M, flags=0x1000 if os.environ.get("NAQS_BENCH_ALLGATHER") else int(os.environ.get("NAQS_BENCH_EXCHANGE_FLAGS", "0"), 0))
         elif world > 1 and allreduce_table:
             # small key space: the direct-address table itself is all-reduced (8 * 2^N bytes, independent of the rank count);
             # psi is a function of the state, so copies of a key on several ranks are identical

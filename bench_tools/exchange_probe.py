@@ -37,7 +37,7 @@ for tag, M in (("dense_1e6", 1_000_000), ("sparse_1e4", 10_000)):
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            comm.exchange(table, d_k, d_p, flags=flags)
+            comm.exchange(table, d_k, d_p, max_local=M, flags=flags)
             e1.record()
             e1.synchronize()
             if it >= 5:

@@ -132,8 +132,12 @@ int naqs_comm_info(const naqs_comm_t* c, int* world_size, int* rank);
  *     rank r ORs slice r of every peer's table into its own (P2P loads) and stores the merged slice into every table (P2P
  *     stores); two flag round trips, volume 2 (world - 1) / world tables per rank whatever the rank count.
  *     NAQS_EXCHANGE_REDUCE selects round 1's form (fill with -0.0f, scatter, ncclAllReduce MAX on the int32 bit patterns).
- *   otherwise: NCCL all-gather of the shards padded to max_local (the largest shard, the same value on every rank), then one
- *     naqs_lookup_build with NAQS_LOOKUP_DUPLICATES_EQUAL; `flags` may carry NAQS_LOOKUP_DENSE / _HASH. */
+ *   otherwise (hash lookups): every rank stores its shard, padded to the slot capacity with out-of-range keys, into its slot of
+ *     every rank's gather buffer (push kernel over peer memory, one flag round trip), then one naqs_lookup_build with
+ *     NAQS_LOOKUP_DUPLICATES_EQUAL over all slots; `flags` may carry NAQS_LOOKUP_DENSE / _HASH.  NAQS_EXCHANGE_GATHER selects
+ *     round 1's form (NCCL all-gather of the padded shards).
+ * max_local must be the SAME on every rank (the largest n_local): the choice between merge and push and the slot size of the
+ * gather buffers are derived from it, and ranks that decided differently would wait for each other forever. */
 int naqs_table_exchange(naqs_table_t* t, naqs_comm_t* c, const uint64_t* d_keys, const void* d_psi, int psi_dtype, int64_t n_local,
                         int64_t max_local, int flags, void* stream);
 /* In-place all-reduce (sum) of the five statistics sums of naqs_eloc_stats (energy.py:328,372-375).  With a mapped peer

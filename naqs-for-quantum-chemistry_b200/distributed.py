@@ -147,12 +147,18 @@ class Comm:
             _lib.check(lib.naqs_comm_init(C.byref(self._h), _lib.ptr(np.ascontiguousarray(uid)), self.world, self.rank, self.device.index), "naqs_comm_init")
 
     def exchange(self, table, keys, psi, max_local=None, flags=0):
-        """(key, psi) shards of all ranks -> lookup table of `table` (naqs_table_exchange).  max_local: the largest shard size
-        (needed by the all-gather path only; default: this shard's size, i.e. equal shards)."""
+        """(key, psi) shards of all ranks -> lookup table of `table` (naqs_table_exchange).  max_local: the largest shard size of
+        all ranks — every rank must pass the SAME value (it sizes the gather slots and decides merge vs push, a collective
+        decision).  None: it is obtained with one all-reduce (MAX) of the shard sizes; pass it to keep that off the step."""
         from . import _lib
         k = _lib.keys_to_device(keys, table.words, table.device)
         p, code = _lib.psi_to_device(psi, table.device)
         n = k.shape[0]
+        if max_local is None and self.world > 1:
+            backend = dist.get_backend(self.group)
+            m = torch.tensor([n], dtype=torch.int64, device=table.device if backend == "nccl" else "cpu")
+            dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
+            max_local = int(m.item())
         with torch.cuda.device(table.device):
             _lib.check(_lib.load().naqs_table_exchange(table._h, self._h, _lib.ptr(k), _lib.ptr(p), code, n, n if max_local is None else int(max_local), flags,
                                                        _lib.stream_ptr(table.device)), "naqs_table_exchange")
