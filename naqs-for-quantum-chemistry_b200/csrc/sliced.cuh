@@ -215,17 +215,18 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// The try_wait predicate is per LANE and steers a branch inside inline asm, which the compiler's convergence analysis does not
-// see: lanes that observe the phase flip in different polls leave the loop diverged, and the code that follows keeps warp-uniform
-// values (buffer index, record pointer, n_blocks) in UNIFORM registers — shared by the whole warp.  Two halves of a warp at
-// different points of the tile loop then corrupt each other's uniform state (found by compute-sanitizer memcheck, whose
-// instrumentation serialises the lanes: the valid lanes of a partially valid warp read shared memory at n_blocks * buf_bytes).
-// __syncwarp() forces the warp back together before any uniform value is used.
+// One poll of the barrier phase / the spin loop around it.  ptxas treats the try_wait predicate as warp-uniform (no BSSY / BSYNC
+// around the loop in the SASS, whether the branch is written in C++ or inside the asm) and removes any __syncwarp() placed after it.
+// compute-sanitizer memcheck reports, for the 128-bit hash walk only, lanes of one warp reading shared memory through stale
+// warp-uniform registers (open); plain hardware reproduces the oracle on every row.
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done != 0u;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
-        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-    __syncwarp();
+    while (!mbar_try_wait(bar, parity)) { }
 }
 // TMA 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -408,7 +409,6 @@ __device__ __forceinline__ void heavy_lookup(int n, const double (&h)[B], const 
             }
         }
     }
-    __syncwarp();  // the probe loops above are per lane: back together before the caller touches warp-uniform state (see mbar_wait)
 }
 
 // pending RECORDS per thread (hash mode): 8-byte entries {parity word, survivor mask | record}; a ring (FIFO), so a thread
@@ -511,7 +511,6 @@ eloc_sliced_kernel(SlicedView sv, const __grid_constant__ ChunkBounds chunks, ui
             task = s_task;
         }
         if (task >= n_tasks) break;
-        __syncwarp();  // the per-lane tail of the previous task (stores of the valid lanes) is over before uniform values are formed
         const int chunk = (int)(task / n_blocks);
         const int64_t blk = task - (int64_t)chunk * n_blocks;
         const int tile_lo = chunks.lo[chunk], tile_hi = chunks.lo[chunk + 1];
@@ -565,10 +564,7 @@ eloc_sliced_kernel(SlicedView sv, const __grid_constant__ ChunkBounds chunks, ui
         uint32_t qhead = 0, qtail = 0;        // byte offsets (multiples of QSTRIDE, free-running); the ring holds (qtail - qhead) / QSTRIDE entries
         uint32_t cur_P = 0, cur_meta = 0;     // entry being resolved: (cur_meta & 0xff) = couplings still pending
         // one coupling per lane: take the lowest pending group of the current entry (refilled from the ring when exhausted)
-        // (__syncwarp at the top of the two hash-walk steps: the record pointer, the buffer index and the loop counters live in
-        // UNIFORM registers, so the lanes of a warp must never be at different records — see mbar_wait)
         auto resolve_round = [&](const unsigned char* __restrict__ buf) {
-            __syncwarp();
             if ((cur_meta & 0xffu) == 0u && qhead != qtail) {
                 const uint2 e = *reinterpret_cast<const uint2*>(q0 + (qhead & qwrap));
                 qhead += QSTRIDE;
@@ -598,7 +594,6 @@ eloc_sliced_kernel(SlicedView sv, const __grid_constant__ ChunkBounds chunks, ui
         auto light_record = [&](const unsigned char* __restrict__ buf, const unsigned char* __restrict__ rec, uint32_t rec_meta, auto kind_tag) {
             constexpr bool KB = decltype(kind_tag)::value;
             constexpr int G = KB ? 5 : 8, LB = KB ? 6 : 4;
-            __syncwarp();
             const uint32_t P = parity_word<NN>(rec, nib);
             const uint32_t* Z = reinterpret_cast<const uint32_t*>(rec + 64 * NN + ZOFF);
             uint32_t z[10];
@@ -699,7 +694,6 @@ eloc_sliced_kernel(SlicedView sv, const __grid_constant__ ChunkBounds chunks, ui
             } else {
                 const unsigned char* p = buf;
                 for (uint32_t b = 0; b < tl_count; ++b) {
-                    __syncwarp();
                     const uint32_t* hdr = reinterpret_cast<const uint32_t*>(p);
                     const uint32_t n_words = hdr[0];
                     double acc = 0.0;  // every blob is self-contained: sum_u-blobs (H_blob * psi(s ^ u)) — tiles of one group may run in different CTAs (table chunks)
