@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, step O (1 GPU): final suite + bench lines + launch list (the ncu --set full captures of the unchanged hot kernels are those of step F)
+# (1 GPU) final suite + bench lines + launch list (the ncu --set full captures of the unchanged hot kernels are those of step F)
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -q -m gpu --maxfail=10 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -6 gpurun_out/pytest_gpu.log | cut -c1-250

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, step F: full GPU suite + default bench line + Li2O / H2O lines + launch list + ncu --set full of both hot kernels
+# full GPU suite + default bench line + Li2O / H2O lines + launch list + ncu --set full of both hot kernels
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -q -m gpu --maxfail=10 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -15 gpurun_out/pytest_gpu.log | cut -c1-250

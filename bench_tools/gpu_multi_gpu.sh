@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, multi-GPU step: [2-GPU parity tests] + weak / strong bench lines for the N given (bench self-checks against a single-rank recomputation)
-# usage: bash bench_tools/gpu_r2m.sh <tag> "<N list>" "<workload:mode list>" [pytest]
+# usage: bash bench_tools/gpu_multi_gpu.sh <tag> "<N list>" "<workload:mode list>" [pytest]
 TAG=${1:-r2m}; NS=${2:-"2"}; JOBS=${3:-"n2_1e6:weak n2_1e6:strong li2o_1e5:strong"}; PYT=${4:-}
 NG=$(nvidia-smi -L | wc -l)
 mkdir -p gpurun_out

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, step K (8 GPUs): exchange probe + weak / strong lines at N = 8 (merge vs NCCL all-reduce for the dense-shard exchange)
+# (8 GPUs) exchange probe + weak / strong lines at N = 8 (merge vs NCCL all-reduce for the dense-shard exchange)
 mkdir -p gpurun_out
 NG=$(nvidia-smi -L | wc -l)
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29801 bench_tools/exchange_probe.py 2>/dev/null | tail -1 | tee gpurun_out/r2k_exchange_probe_g$NG.json

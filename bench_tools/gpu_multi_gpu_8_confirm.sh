@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, step P (8 GPUs): push-gather exchange at N = 8 (Li2O strong / weak), N2 weak at 2 and strong at 4 with the final merge kernel
+# (8 GPUs) push-gather exchange at N = 8 (Li2O strong / weak), N2 weak at 2 and strong at 4 with the final merge kernel
 mkdir -p gpurun_out
 run() {  # tag n workload mode
   local out=gpurun_out/r2p_$1_$3_$4_g$2

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, step Q (1 GPU): final suite after the warp-reconvergence points + N2 / Li2O / synthetic-127 lines
+# (1 GPU) final suite after the warp-reconvergence points + N2 / Li2O / synthetic-127 lines
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -q -m gpu --maxfail=10 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log | cut -c1-250

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, step N (1 GPU): BASELINE config 5 grid in one process + ncu --set full of the 128-bit hash walk
+# (1 GPU) BASELINE config 5 grid in one process + ncu --set full of the 128-bit hash walk
 mkdir -p gpurun_out
 timeout 1500 python bench_tools/sweep.py --out gpurun_out/sweep.jsonl 2>&1 | tail -40
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:eloc_sliced -s 3 -c 1 -o gpurun_out/synth127 \
