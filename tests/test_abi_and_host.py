@@ -207,6 +207,45 @@ print("ok")
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/optimizer"), reason="reference tree not present (GPU box)")
+def test_install_device_resident_patches_every_hilbert_flavour():
+    """install(device_resident=True): state2idx is defined per Hilbert flavour (hilbert.py:344, 573, 833) and to_idx_array once in
+    the base class (:85) — every concrete state2idx and the base to_idx_array must be wrapped (a CUDA tensor reaching an unwrapped
+    one fails inside the reference with a device mismatch), host inputs must still take the reference's own code, and
+    _SGD_step must be the fused step."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, types
+sys.path.insert(0, "%s")
+from oracle import ref_harness
+ref_harness.install_stubs()
+import numpy as np, torch
+import naqs_b200
+assert naqs_b200.install("/root/reference")                                  # the twins make `import src.utils.hilbert` possible
+import src.utils.hilbert as hil
+orig = {n: getattr(hil, n).__dict__["state2idx"] for n in ("_HilbertFull", "_HilbertRestricted", "_HilbertPartiallyRestricted")}
+orig_arr = hil._HilbertBase.__dict__["to_idx_array"]
+assert naqs_b200.install("/root/reference", device_resident=True)
+for n, f in orig.items():
+    g = getattr(hil, n).__dict__["state2idx"]
+    assert g is not f and getattr(g, "__wrapped__", None) is f, n          # wrapped, and the host path is the reference's own function
+assert hil._HilbertBase.__dict__["to_idx_array"].__wrapped__ is orig_arr
+assert getattr(hil._HilbertBase.__dict__["state2idx"], "__isabstractmethod__", False)   # the abstract declaration is left alone
+# host tensors still run the reference's code (hilbert.py:573-581) through the wrapper
+me = types.SimpleNamespace(_idx_basis_vec=torch.tensor([2 ** n for n in range(6)]), to_idx_tensor=lambda x: torch.as_tensor(x).long())
+st = torch.tensor([[1, -1, 1, -1, -1, 1], [-1, -1, -1, 1, 1, -1]], dtype=torch.int8)
+assert hil._HilbertRestricted.state2idx(me, st).reshape(-1).tolist() == [1 + 4 + 32, 8 + 16]
+import src.optimizer.energy as E
+assert E.OptimizerBase._SGD_step is naqs_b200.energy.sgd_step
+import src.naqs.wavefunction as wf
+assert hasattr(wf.NAQSComplex_NADE_orbitals.sample, "__wrapped__")
+print("ok")
+''' % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_reference_backend_switch_leaves_reference_alone(monkeypatch):
     monkeypatch.setenv("NAQS_ELOC_BACKEND", "reference")
     assert naqs_b200.install("/nonexistent") is False
