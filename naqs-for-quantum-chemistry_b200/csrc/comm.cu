@@ -16,6 +16,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -109,6 +110,11 @@ struct naqs_comm {
     char** d_gpeer = nullptr;
     int* d_gdone = nullptr;
     unsigned epoch_gather = 0;
+    // peer mapping (CUDA IPC) is probed once, collectively; without it every exchange takes its NCCL form
+    int ipc_state = 0;              // 0 = not probed, 1 = available on every rank, -1 = unavailable (or NAQS_COMM_NO_IPC)
+    void* d_local_tbl_raw = nullptr;  // NCCL all-reduce form without a peer region: a local table aligned to its size
+    float2* d_local_tbl = nullptr;
+    int64_t local_tbl_entries = 0;
 };
 
 namespace naqs {
@@ -296,6 +302,48 @@ static int comm_sync_barrier(naqs_comm* c, cudaStream_t st) {  // host-visible b
     NAQS_CUDA(cudaStreamSynchronize(st));
     cudaFree(d);
     return NAQS_OK;
+}
+
+// One-time collective probe: can every rank map every peer's memory through CUDA IPC?  (Containers without a shared IPC namespace,
+// GPUs without peer access.)  The answer is all-reduced (MIN), so all ranks take the same exchange forms afterwards.
+static int ipc_probe(naqs_comm* c, cudaStream_t st) {
+    if (c->ipc_state != 0) return NAQS_OK;
+    int ok = getenv("NAQS_COMM_NO_IPC") ? 0 : 1;
+    void* buf = nullptr;
+    cudaIpcMemHandle_t mine;
+    std::memset(&mine, 0, sizeof(mine));
+    if (ok && (cudaMalloc(&buf, 1 << 16) != cudaSuccess || cudaIpcGetMemHandle(&mine, buf) != cudaSuccess)) { ok = 0; cudaGetLastError(); }
+    cudaIpcMemHandle_t* d_h = nullptr;
+    NAQS_CUDA(cudaMalloc((void**)&d_h, sizeof(mine) * c->world));
+    NAQS_CUDA(cudaMemcpyAsync(d_h + c->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+    NAQS_NCCL(nccl_api().AllGather(d_h + c->rank, d_h, sizeof(mine), ncclUint8, c->nccl, st));
+    std::vector<cudaIpcMemHandle_t> all((size_t)c->world);
+    NAQS_CUDA(cudaMemcpyAsync(all.data(), d_h, sizeof(mine) * c->world, cudaMemcpyDeviceToHost, st));
+    int* d_ok = nullptr;
+    NAQS_CUDA(cudaMalloc((void**)&d_ok, sizeof(int)));
+    NAQS_CUDA(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, st));
+    NAQS_NCCL(nccl_api().AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, c->nccl, st));   // did every rank export a handle?
+    int all_exported = 0;
+    NAQS_CUDA(cudaMemcpyAsync(&all_exported, d_ok, sizeof(int), cudaMemcpyDeviceToHost, st));
+    NAQS_CUDA(cudaStreamSynchronize(st));
+    ok = all_exported;
+    std::vector<void*> opened;
+    if (ok)
+        for (int r = 0; r < c->world && ok; ++r) {
+            if (r == c->rank) continue;
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+            else opened.push_back(p);
+        }
+    NAQS_CUDA(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, st));
+    NAQS_NCCL(nccl_api().AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, c->nccl, st));   // could every rank map every peer?
+    NAQS_CUDA(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, st));
+    NAQS_CUDA(cudaStreamSynchronize(st));
+    for (void* p : opened) cudaIpcCloseMemHandle(p);
+    int rc = comm_sync_barrier(c, st);   // every mapping is closed before the probe buffers are freed
+    cudaFree(d_h); cudaFree(d_ok); cudaFree(buf);
+    c->ipc_state = ok ? 1 : -1;
+    return rc;
 }
 
 // (Re)create the peer-mapped region for direct-address tables of `entries` complex64 values.  Collective and synchronous:
@@ -488,7 +536,7 @@ int naqs_comm_destroy(naqs_comm_t* c) {
     for (int r = 0; r < (int)c->gpeer.size(); ++r)
         if (r != c->rank && c->gpeer[(size_t)r]) cudaIpcCloseMemHandle(c->gpeer[(size_t)r]);
     cudaFree(c->region); cudaFree(c->d_peer); cudaFree(c->d_table_off); cudaFree(c->d_done); cudaFree(c->d_gather);
-    cudaFree(c->gregion); cudaFree(c->d_gpeer); cudaFree(c->d_gdone);
+    cudaFree(c->gregion); cudaFree(c->d_gpeer); cudaFree(c->d_gdone); cudaFree(c->d_local_tbl_raw);
     if (c->own_nccl && c->nccl) nccl_api().CommDestroy(c->nccl);
     delete c;
     return NAQS_OK;
@@ -511,16 +559,33 @@ int naqs_table_exchange(naqs_table_t* t, naqs_comm_t* c, const uint64_t* d_keys,
     const bool dense_push = t->nw32 == 1 && t->n_qubits <= 22 && t->n_qubits >= 5 && psi_dtype == NAQS_C64 && t->algo == 0 && !(flags & NAQS_EXCHANGE_GATHER);
     if (dense_push) {
         const int64_t entries = 1ll << t->n_qubits;
-        int rc = ensure_region(c, entries, st);
+        int rc = c->world > 1 ? ipc_probe(c, st) : NAQS_OK;
         if (rc) return rc;
+        const bool no_ipc = c->world > 1 && c->ipc_state < 0;
+        if (!no_ipc) {
+            rc = ensure_region(c, entries, st);
+            if (rc) return rc;
+        }
         // dense shards -> merge of the tables over peer memory (NAQS_EXCHANGE_REDUCE: the NCCL all-reduce (MAX) of round 1 instead);
         // sparse shards -> push
         const bool dense_shards = c->world > 1 && !(flags & NAQS_EXCHANGE_PUSH) &&
                                   ((flags & (NAQS_EXCHANGE_REDUCE | NAQS_EXCHANGE_MERGE)) || (double)max_local * (c->world - 1) > 0.5 * (double)entries);
-        const bool reduce = dense_shards && (flags & NAQS_EXCHANGE_REDUCE) != 0;
+        const bool reduce = no_ipc || (dense_shards && (flags & NAQS_EXCHANGE_REDUCE) != 0);  // no peer mapping: always the NCCL form
         const bool merge = dense_shards && !reduce && entries >= 2 * (int64_t)c->world;
         if (reduce) {
-            float2* tbl = reinterpret_cast<float2*>(c->region + c->info[(size_t)c->rank].table_off[0] + 2 * (size_t)entries * sizeof(float2));
+            float2* tbl;
+            if (no_ipc) {
+                if (c->local_tbl_entries < entries) {
+                    cudaFree(c->d_local_tbl_raw); c->d_local_tbl_raw = nullptr; c->d_local_tbl = nullptr; c->local_tbl_entries = 0;
+                    const size_t tb = (size_t)entries * sizeof(float2);
+                    NAQS_CUDA(cudaMalloc(&c->d_local_tbl_raw, 2 * tb));
+                    c->d_local_tbl = reinterpret_cast<float2*>(((uintptr_t)c->d_local_tbl_raw + tb - 1) & ~(uintptr_t)(tb - 1));
+                    c->local_tbl_entries = entries;
+                }
+                tbl = c->d_local_tbl;
+            } else {
+                tbl = reinterpret_cast<float2*>(c->region + c->info[(size_t)c->rank].table_off[0] + 2 * (size_t)entries * sizeof(float2));
+            }
             fill_absent_kernel<<<4 * 148, 256, 0, st>>>(reinterpret_cast<int4*>(tbl), entries / 2);
             NAQS_LAUNCHED();
             if (n_local > 0) {
@@ -564,7 +629,8 @@ int naqs_table_exchange(naqs_table_t* t, naqs_comm_t* c, const uint64_t* d_keys,
     NAQS_REQUIRE(max_local >= n_local, NAQS_ERR_ARG, "naqs_table_exchange: max_local must be the largest shard size of all ranks");
     if (c->world == 1)
         return naqs_lookup_build(t, d_keys, d_psi, psi_dtype, n_local, (flags & 0xff) | NAQS_LOOKUP_DUPLICATES_EQUAL, st);
-    if (!(flags & NAQS_EXCHANGE_GATHER)) {
+    if (int rc_p = ipc_probe(c, st)) return rc_p;
+    if (!(flags & NAQS_EXCHANGE_GATHER) && c->ipc_state > 0) {
         const size_t kb = (size_t)8 * t->words, pb = psi_dtype == NAQS_C64 ? 8 : 16;
         int rc = ensure_gather_region(c, max_local, kb, pb, st);
         if (rc) return rc;
