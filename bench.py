@@ -320,17 +320,17 @@ def cpu_baseline_sample(wl, sample, reps=2):
     M = min(sample, len(wl["states"]))
     path = ref_path.ReferencePath(wl["xy"], wl["yz"], wl["c"], wl["N"], wl["na"], wl["nb"])
     st, psi = wl["states"][:M].astype(np.int64).reshape(-1), wl["psi"][:M]
-    best = None
+    best, eloc = None, None
     for _ in range(reps):
         path.reset()
         t0 = time.perf_counter()
-        path.local_energy(st, psi)
+        eloc = path.local_energy(st, psi)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     K = len(wl["c"])
     return {"value": M * K / best, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
             "sample": f"first {M} states of the workload, K={K}, cold H cache, best of {reps}: {best:.2f} s "
-                      f"(reference Cython kernels from oracle/_ref + numpy/scipy orchestration of hamiltonian.py:272-370)"}
+                      f"(reference Cython kernels from oracle/_ref + numpy/scipy orchestration of hamiltonian.py:272-370)"}, (st, psi, eloc)
 
 
 def measure_extras(naqs_b200, dev, args):
@@ -754,10 +754,18 @@ def main():
             extras = measure_extras(naqs_b200, dev, args)
         except Exception as e:  # noqa: BLE001
             extras = {"error": repr(e)}
-    cpu = None
+    cpu, parity_vs_cpu = None, None
     if world == 1 and args.cpu_sample > 0:
         try:
-            cpu = cpu_baseline_sample(wl, args.cpu_sample)
+            cpu, (c_st, c_psi, c_eloc) = cpu_baseline_sample(wl, args.cpu_sample)
+            # the same sample (table = the sample itself, as the reference path computed it) through the device path: the bench
+            # line carries its own parity figure against the reference kernels (bar: 1e-12 relative, north_star)
+            try:
+                g = _lib.complex_from_pairs(table.local_energy(np.asarray(wl["states"])[: len(c_psi)], c_psi, assume_unique=not dedup))
+                rel = np.abs(g - np.asarray(c_eloc)) / np.maximum(np.abs(np.asarray(c_eloc)), 1e-300)
+                parity_vs_cpu = {"rows": int(len(g)), "max_rel_err": float(rel.max()), "ok": bool(rel.max() <= 1e-12)}
+            except Exception as e:  # noqa: BLE001
+                parity_vs_cpu = {"error": repr(e)}
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -771,7 +779,8 @@ def main():
                        "l2": "256 MB device memset between timed steps (L2 flush, untimed)", "timing": "CUDA events per step on the launching stream, max over ranks"},
             "clocks": clk_summary, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_pipe": roofline_pipe,
             "cpu_baseline": cpu, "other_configs": extras,
-            "check": {"mean_eloc_re": float(stats[1] / stats[0]), "n": int(stats[4]), "multi_gpu_vs_single_rank": mgpu_check}}
+            "check": {"mean_eloc_re": float(stats[1] / stats[0]), "n": int(stats[4]), "multi_gpu_vs_single_rank": mgpu_check,
+                      "vs_cpu_baseline_sample": parity_vs_cpu}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
