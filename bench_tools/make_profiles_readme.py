@@ -107,6 +107,7 @@ if os.path.exists(sw):
             w(f"| {d['mask_bits']} | {d['K']} | {d['M']} | {d['value']:.3e} | {d['ms_per_step']:.3f} | {d['kernel_ms']:.3f} | {d['roofline']['frac']:.3f} |")
 w("\n## Other files")
 w(f"`{R}_pytest_gpu_*.log` — GPU suite logs; `pipe_peaks_r01.json` — measured POPC / LOP3 / IMAD / DADD / gather ceilings (`bench_tools/pipe_peaks.cu`); "
-  "`r01_sanitize_*.log` — compute-sanitizer memcheck + racecheck of round 1.\n")
+  f"`{R}_sanitize_racecheck.log` — compute-sanitizer racecheck, 32 tests, 0 hazards; `{R}_sanitize_memcheck.log` — memcheck: clean except the open report on the "
+  "128-bit hash walk (DESIGN.md §9; excerpt of the first two records); `r01_sanitize_*.log` — round 1.\n")
 open(os.path.join(P, "README.md"), "w").write("\n".join(out) + "\n")
 print("\n".join(out)[:1500])
